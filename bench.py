@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""bench.py — env-steps/s of the fused Block Blast step kernel (BASELINE.json config 3:
+random valid-action policy, 262,144 envs per GPU), with roofline, CPU baseline and the
+end-to-end number through the drop-in API.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = ONE launch of the fused K1 kernel over ONE batch of `--envs` environments
+(policy action pick, placement, line clears, scoring, Philox trio regeneration with the
+solvability search, game over, reward, auto-reset, next mask), reading and writing the full
+packed protocol (129 algorithmic bytes per env-step).  To keep every launch HBM-cold the
+bench rotates over `--batches` independent env batches whose combined footprint exceeds the
+126 MB L2 (stated in config.l2).  Weak scaling: every rank owns its own batches; there is no
+data-path collective (envs are independent), only the timing barrier.
+
+The reference arm (--impl reference) times the CPU restatement of the reference's
+VectorizedBlockBlastEnv(64) + sample_valid_actions loop (oracle/bb_oracle.py, same cell-grid
+algorithm and serial per-env Python loop as the reference; the Python reference itself cannot
+travel to the GPU box) on all host cores (one process per core).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 129          # SURVEY.md §8d / DESIGN.md: 48 R + 48 W + 4 + 4 + 1 + 24
+STATE_BYTES, OUT_BYTES = 48, 33
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def _py_port_worker(args):
+    """One process: the Python oracle port of VectorizedBlockBlastEnv(64) + sample_valid_actions
+    (method of the reference's scripts/benchmark.py:101-144)."""
+    seed, n_envs, seconds, min_steps = args
+    import numpy as np
+    from oracle import bb_oracle as O
+    rng = np.random.RandomState(seed)
+    envs = [O.Env(seed=seed * 1000 + i, rng_factory=O.numpy_rng_factory) for i in range(n_envs)]
+    vec = O.VecEnv(envs)
+    vec.reset()
+    for _ in range(2):
+        vec.step(vec.sample_valid_actions(rng))
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < min_steps or time.perf_counter() - t0 < seconds:
+        vec.step(vec.sample_valid_actions(rng))
+        steps += 1
+    return steps * n_envs, time.perf_counter() - t0
+
+
+def cpu_python_port(n_procs, seconds, n_envs=64, min_steps=1):
+    import multiprocessing as mp
+    if n_procs == 1:
+        res = [_py_port_worker((0, n_envs, seconds, min_steps))]
+    else:
+        with mp.get_context("fork").Pool(n_procs) as pool:
+            res = pool.map(_py_port_worker, [(k, n_envs, seconds, min_steps) for k in range(n_procs)])
+    return sum(r[0] for r in res) / max(r[1] for r in res), sum(r[0] for r in res)
+
+
+def cpu_c_port(n_threads, seconds, n_envs=4096):
+    """The plain-C oracle port, random-valid rollout, OpenMP over envs."""
+    import numpy as np
+    from bbgpu import philox
+    from oracle import bb_oracle_c as OC
+    chunk = 64
+    streams = philox.candidate_trios(42, np.arange(n_envs), 4096)
+    env = OC.CVecEnv(streams, n_threads=n_threads)
+    rs = np.random.RandomState(0)
+    words = rs.randint(0, 2 ** 32, size=(chunk, n_envs), dtype=np.uint64).astype(np.uint32)
+    env.random_rollout(8, words)
+    t0 = time.perf_counter()
+    done = 0
+    while time.perf_counter() - t0 < seconds:
+        d, _, _ = env.random_rollout(chunk, words)
+        done += d
+        if env.stats()[:, 7].max() > 3500:      # candidate streams nearly used up: restart them
+            env = OC.CVecEnv(streams, n_threads=n_threads)
+    return done / (time.perf_counter() - t0), done
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = 64
+    per_step_s = 0.06                      # ~64 envs x ~1 ms per Python env-step
+    budget = min(150.0, max(5.0, (args.steps + args.warmup) * per_step_s))
+    # warm-up + timed steps folded into a time-bounded run per process
+    t0 = time.perf_counter()
+    value, total = cpu_python_port(cores, budget, n_envs=n_envs, min_steps=max(1, min(args.steps, 50)))
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs * cores / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": "random valid-action policy, VectorizedBlockBlastEnv(64) per process, "
+                                   "%d processes (one per host core)" % cores,
+                       "step": "one 64-env vec step per process (bounded sample of config 3)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d env-steps in %.1f s: oracle/bb_oracle.py (Python restatement of the "
+                                       "reference's cell-grid engine, serial 64-env loop) x %d processes"
+                                       % (total, wall, cores)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=262144, help="envs per batch (= per launch) per GPU")
+    ap.add_argument("--batches", type=int, default=8, help="independent env batches rotated per GPU (L2-cold launches)")
+    ap.add_argument("--preroll", type=int, default=64, help="untimed random steps to reach the steady-state mix")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bbgpu import capi
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.lib()
+
+    n, M, K, W = args.envs, args.batches, args.steps, max(3, args.warmup)
+    seed = 42
+    # independent batches; global env ids are disjoint across batches and ranks
+    envs, outs = [], []
+    for b in range(M):
+        envs.append(capi.EnvHandle(n, seed, global_env_offset=(rank * M + b) * n))
+        outs.append(dict(actions=torch.zeros(n, dtype=torch.int32, device=dev),
+                         rewards=torch.zeros(n, dtype=torch.float32, device=dev),
+                         term=torch.zeros(n, dtype=torch.uint8, device=dev),
+                         mask=torch.zeros((3, n), dtype=torch.int64, device=dev)))
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    for e in envs:
+        e.step_random(args.preroll)          # desynchronise episodes (all envs start in lockstep)
+    torch.cuda.synchronize()
+
+    def launch(k):
+        b = k % M
+        o = outs[b]
+        envs[b].step_random(1, o["actions"], o["rewards"], o["term"], o["mask"], stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(W):
+        launch(k)
+    barrier()
+    stats.zero_()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for k in range(K):
+        launch(W + k)
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    s = stats.cpu().tolist()
+    assert s[0] == n * K, "kernel did not process the expected number of env-steps"
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * n * K / (ms_max * 1e-3)
+
+    # L2-warm variant (single batch, state+outputs 21 MB stay in L2): reported beside, not as value
+    for k in range(20):
+        envs[0].step_random(1, outs[0]["actions"], outs[0]["rewards"], outs[0]["term"], outs[0]["mask"], stats)
+    barrier()
+    ev0.record()
+    kw = min(K, 1000)
+    for k in range(kw):
+        envs[0].step_random(1, outs[0]["actions"], outs[0]["rewards"], outs[0]["term"], outs[0]["mask"], stats)
+    ev1.record()
+    barrier()
+    ms_warm = ev0.elapsed_time(ev1)
+
+    # fused rollout: ONE launch runs 256 steps with the env state in registers
+    ev0.record()
+    envs[0].step_random(256, None, None, None, None, stats)
+    ev1.record()
+    barrier()
+    ms_fused = ev0.elapsed_time(ev1)
+
+    # ------------------------------------------------------------------ e2e through the drop-in API
+    Ke = args.e2e_steps or min(K, 100)
+    venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n)
+    venv.reset()
+    for _ in range(3):
+        venv.step(venv.sample_valid_actions())
+    barrier()
+    t0 = time.perf_counter()
+    n_term = 0
+    for _ in range(Ke):
+        a = venv.sample_valid_actions()                    # kernel + D2H 4 B/env (numpy actions, as the reference)
+        obs, rew, term, trunc, infos = venv.step(a)        # H2D 4 B/env, K1, D2H packed obs 41 B/env
+        n_term += int(term.sum())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / float(te.item())
+    h2d = 4 * n
+    d2h = 4 * n + (4 + 1 + 8 + 4 + 24 + 4 + 4) * n
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        per_launch_s = ms_max * 1e-3 / K
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "random valid-action policy, %d envs per GPU per launch (BASELINE config 3)" % n,
+                       "envs_per_gpu_per_launch": n, "batches_rotated": M, "seed": seed,
+                       "l2": "rotating %d independent env batches per GPU: %.0f MB of state+outputs > 126 MB L2, "
+                             "every launch reads its state from HBM" % (M, M * n * (STATE_BYTES + OUT_BYTES) / 1e6),
+                       "protocol": "packed: state 48 B R+W, action 4 B, reward 4 B, terminated 1 B, mask 24 B",
+                       "parallelism": "env shards per GPU, no data-path collective"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "bb_step_kernel<true>",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
+                         "launch_us": per_launch_s * 1e6},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "api": "VectorizedBlockBlastEnv(output='numpy'): sample_valid_actions() + step(actions), "
+                                        "pinned host buffers, packed obs expanded lazily on host"},
+            "clocks": clocks,
+            "extra": {"l2_warm_single_batch_env_steps_per_sec": n * kw / (ms_warm * 1e-3),
+                      "fused_256_step_launch_env_steps_per_sec": n * 256 / (ms_fused * 1e-3),
+                      "episodes": s[1], "mean_episode_len": (s[3] / s[1]) if s[1] else None,
+                      "mean_final_score": (s[2] / s[1]) if s[1] else None, "wall_s_timed_region": wall},
+        }
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v_py, tot_py = cpu_python_port(1, args.cpu_seconds)
+            v_c, tot_c = cpu_c_port(cores, min(args.cpu_seconds, 10.0))
+            line["cpu_baseline"] = {"value": v_py, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d env-steps: oracle/bb_oracle.py VecEnv(64) + sample_valid_actions, "
+                                              "serial Python like the reference (wrappers.py:93-108)" % tot_py}
+            line["cpu_baseline_c_port"] = {"value": v_c, "unit": UNIT, "cores": cores, "kind": "port",
+                                           "sample": "%d env-steps: oracle/bb_oracle.c random-valid rollout, 4096 envs, "
+                                                     "OpenMP over all host cores" % tot_c}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+"""ctypes binding of libbbgpu.so (C ABI: include/bbgpu.h).
+
+Loads the in-tree CUDA library and fails loudly when it is missing — there is no CPU
+fallback anywhere in this package.  PyTorch is used only for device memory and streams:
+every ``torch.Tensor`` argument is passed as ``tensor.data_ptr()``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libbbgpu.so")
+
+BB_F32, BB_BF16, BB_U8 = 0, 1, 2
+ENV_RESEED_ON_RESET = 1
+ENV_NO_AUTO_RESET = 2
+ABI_VERSION = 1
+
+REWARD_KEYS = ("line_clear_base", "block_placed", "game_over_penalty", "hole_penalty",
+               "center_bonus", "combo_multiplier_bonus", "survival_bonus")
+REWARD_DEFAULTS = dict(line_clear_base=1.0, block_placed=0.01, game_over_penalty=-1.0,
+                       hole_penalty=-0.05, center_bonus=0.02, combo_multiplier_bonus=0.5,
+                       survival_bonus=0.001)   # reference block_blast_env.py:63-71
+
+#: 48-byte per-env record of bb_env_get_state / bb_env_set_state
+STATE_DTYPE = np.dtype([("board", "<u8"), ("pieces", "<u4"), ("aux", "<u4"), ("score", "<i4"),
+                        ("streak", "<i4"), ("moves", "<i4"), ("lines_total", "<i4"),
+                        ("max_streak", "<i4"), ("blocks_total", "<i4"), ("draw_ctr", "<u4"),
+                        ("policy_ctr", "<u4")])
+
+_lib = None
+
+
+class BBGpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises if it has not been built (run ``python -m bbgpu.build`` or
+    ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BBGpuError("libbbgpu.so not found at %s: the CUDA extension must be built "
+                         "(python __graft_entry__.py build); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, u64, i32, u32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_uint32
+    L.bb_version.restype = C.c_int
+    L.bb_last_error.restype = C.c_char_p
+    L.bb_piece_table.argtypes = [vp, vp, vp]
+    L.bb_env_create.argtypes = [C.POINTER(vp), i64, u64, i64, vp, u32]
+    L.bb_env_destroy.argtypes = [vp]
+    L.bb_env_num_envs.argtypes = [vp]
+    L.bb_env_num_envs.restype = i64
+    L.bb_env_reset.argtypes = [vp, vp, vp, vp]
+    L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.bb_env_observe.argtypes = [vp, vp, vp, vp, vp]
+    L.bb_env_get_state.argtypes = [vp, vp, vp]
+    L.bb_env_set_state.argtypes = [vp, vp, vp]
+    L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
+    L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
+    L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
+    if L.bb_version() != ABI_VERSION:
+        raise BBGpuError("libbbgpu.so ABI %d != expected %d" % (L.bb_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise BBGpuError("libbbgpu: %s (code %d)" % (lib().bb_last_error().decode(), rc))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def reward_cfg_array(reward_config=None):
+    cfg = dict(REWARD_DEFAULTS)
+    if reward_config:
+        cfg.update(reward_config)
+    return np.array([cfg[k] for k in REWARD_KEYS], dtype=np.float64)
+
+
+def piece_table():
+    masks = np.zeros(37, np.uint64)
+    inb = np.zeros(37, np.uint64)
+    nblk = np.zeros(37, np.uint8)
+    check(lib().bb_piece_table(ptr(masks), ptr(inb), ptr(nblk)))
+    return masks, inb, nblk
+
+
+class EnvHandle:
+    """Owns one ``bb_env`` on the current CUDA device."""
+
+    def __init__(self, n_envs, seed=0, global_env_offset=0, reward_config=None, flags=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise BBGpuError("bbgpu needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.n = int(n_envs)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        cfg = reward_cfg_array(reward_config)
+        check(lib().bb_env_create(C.byref(h), self.n, int(seed) & (2 ** 64 - 1), int(global_env_offset),
+                                  ptr(cfg), int(flags)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bb_env_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, reset_mask=None, mask_out=None):
+        check(lib().bb_env_reset(self.h, ptr(reset_mask), ptr(mask_out), current_stream()))
+
+    def step(self, actions, rewards, terminated, mask_out=None, ep_score=None, ep_len=None, info_out=None):
+        check(lib().bb_env_step(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(mask_out),
+                                ptr(ep_score), ptr(ep_len), ptr(info_out), current_stream()))
+
+    def step_random(self, n_steps=1, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
+        check(lib().bb_env_step_random(self.h, int(n_steps), ptr(actions_out), ptr(rewards), ptr(terminated),
+                                       ptr(mask_out), ptr(stats), current_stream()))
+
+    def observe(self, board_out=None, pieces_out=None, mask_out=None):
+        check(lib().bb_env_observe(self.h, ptr(board_out), ptr(pieces_out), ptr(mask_out), current_stream()))
+
+    def get_state(self):
+        rec = np.zeros(self.n, STATE_DTYPE)
+        check(lib().bb_env_get_state(self.h, ptr(rec), current_stream()))
+        return rec
+
+    def set_state(self, rec):
+        rec = np.ascontiguousarray(rec, dtype=STATE_DTYPE)
+        assert rec.shape == (self.n,)
+        check(lib().bb_env_set_state(self.h, ptr(rec), current_stream()))
+
+    def step_host(self, actions, rewards, terminated, board=None, pieces=None, mask=None, ep_score=None, ep_len=None):
+        check(lib().bb_env_step_host(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(board), ptr(pieces),
+                                     ptr(mask), ptr(ep_score), ptr(ep_len), current_stream()))
+
+
+def unpack_obs(board, pieces, mask, mask_stride, obs=None, mask_dense=None, n=None):
+    import torch
+    n = int(board.numel() if n is None else n)
+    obs_dt = BB_BF16 if (obs is not None and obs.dtype == torch.bfloat16) else BB_F32
+    mask_dt = BB_F32 if (mask_dense is not None and mask_dense.dtype == torch.float32) else BB_U8
+    check(lib().bb_unpack_obs(ptr(board), ptr(pieces), ptr(mask), int(mask_stride), ptr(obs), obs_dt,
+                              ptr(mask_dense), mask_dt, n, current_stream()))
+
+
+def masked_sample(logits, mask, mask_stride, seed, call_counter, mode, action, logp=None, entropy=None):
+    import torch
+    n = logits.shape[0]
+    assert logits.is_contiguous() and logits.shape[1] == 192
+    dt = BB_BF16 if logits.dtype == torch.bfloat16 else BB_F32
+    check(lib().bb_masked_sample(ptr(logits), dt, ptr(mask), int(mask_stride), int(seed) & (2 ** 64 - 1),
+                                 int(call_counter), int(mode), ptr(action), ptr(logp), ptr(entropy), n,
+                                 current_stream()))
+
+
+def gae(rewards, values, dones, last_values, gamma, lam, adv, ret, moments=None):
+    T, N = rewards.shape
+    check(lib().bb_gae(ptr(rewards), ptr(values), ptr(dones), ptr(last_values), float(gamma), float(lam),
+                       ptr(adv), ptr(ret), ptr(moments), T, N, current_stream()))

@@ -1,0 +1,38 @@
+// bb_kernels.h — internal declarations shared by the kernel translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bb_rules.cuh"
+
+#define BB_STEP_THREADS 128
+
+// device-side view of a batch of envs (SoA of 16-byte words, see bb_rules.cuh BBState)
+struct BBEnvArrays {
+    uint4* s0;   // board lo, board hi, pieces, aux
+    uint4* s1;   // score, streak, moves, lines_total
+    uint4* s2;   // max_streak, blocks_total, draw_ctr, policy_ctr
+    int64_t n;
+    int64_t env_offset;   // global id of env 0 of this shard
+    uint64_t seed;
+    uint32_t flags;
+};
+
+cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const int32_t* actions,
+                           float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
+                           int32_t* ep_len, uint32_t* info_out, cudaStream_t stream);
+cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps,
+                                  int32_t* actions_out, float* rewards, uint8_t* terminated,
+                                  uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream);
+cudaError_t bb_launch_reset(const BBEnvArrays& E, const uint8_t* reset_mask, uint64_t* mask_out, cudaStream_t stream);
+cudaError_t bb_launch_observe(const BBEnvArrays& E, uint64_t* board_out, uint32_t* pieces_out,
+                              uint64_t* mask_out, cudaStream_t stream);
+
+cudaError_t bb_launch_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask,
+                                 int64_t mask_stride, void* obs_nchw, int obs_dtype, void* mask_dense,
+                                 int mask_dtype, int64_t n, cudaStream_t stream);
+cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
+                                    int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
+                                    int32_t* action, float* logp, float* entropy, int64_t n, cudaStream_t stream);
+cudaError_t bb_launch_gae(const float* rewards, const float* values, const float* dones,
+                          const float* last_values, float gamma, float gamma_lam, float* adv, float* ret,
+                          double* moments, int64_t T, int64_t N, cudaStream_t stream);

@@ -1,0 +1,423 @@
+"""Drop-in mirrors of the reference's environment classes on top of the CUDA env kernels.
+
+``VectorizedBlockBlastEnv``  <- src/environment/wrappers.py:14-141
+``BlockBlastEnv``            <- src/environment/block_blast_env.py:20-323 (single env, no auto-reset)
+
+Same constructor arguments, method names, return arity, shapes and dtypes.  All game logic
+runs in ``libbbgpu.so`` (one fused kernel per vec step); this file only moves buffers and
+reshapes the packed observation into the reference's layout.
+
+Output modes (``output=``):
+  "numpy"   reference-compatible: numpy obs dict / rewards / terminated / truncated / infos.
+            One H2D copy (actions) and one packed D2H copy (41 B/env) per step through
+            ``bb_env_step_host``; the dense float planes are expanded lazily on first access.
+  "torch"   same keys and shapes, CUDA tensors, nothing crosses PCIe (K2 expands on device).
+  "packed"  CUDA tensors in the packed protocol: obs = {'board': int64[N], 'pieces': int32[N],
+            'mask': int64[3,N]} — what the on-device rollout path consumes.
+"""
+import os
+
+import numpy as np
+
+from . import capi
+
+BOARD_SIZE = 8
+NUM_PIECES_PER_TURN = 3
+ACTION_SPACE_SIZE = 192
+
+
+class _Box:
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+
+class _DictSpace:
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+
+def _spaces():
+    obs = _DictSpace({
+        "board": _Box(0.0, 1.0, (8, 8), np.float32),
+        "pieces": _Box(0.0, 1.0, (3, 8, 8), np.float32),
+        "action_mask": _Box(0, 1, (ACTION_SPACE_SIZE,), np.int8),
+    })
+    return obs, _Discrete(ACTION_SPACE_SIZE)
+
+
+_PIECE_PLANES = None
+
+
+def piece_planes():
+    """float32 [38, 8, 8]: piece i drawn at the origin (Piece.to_mask, pieces.py:39-45);
+    index 37 is the all-zero plane of a used piece.  Built from the library's own table."""
+    global _PIECE_PLANES
+    if _PIECE_PLANES is None:
+        masks, _, _ = capi.piece_table()
+        bits = np.unpackbits(masks.view(np.uint8).reshape(37, 8), axis=1, bitorder="little")
+        planes = np.zeros((38, 8, 8), np.float32)
+        planes[:37] = bits.reshape(37, 8, 8)
+        _PIECE_PLANES = planes
+    return _PIECE_PLANES
+
+
+def expand_board(board_u64):
+    b = np.ascontiguousarray(board_u64, dtype=np.uint64)
+    return np.unpackbits(b.view(np.uint8).reshape(-1, 8), axis=1, bitorder="little").reshape(-1, 8, 8).astype(np.float32)
+
+
+def expand_pieces(pieces_u32):
+    p = np.ascontiguousarray(pieces_u32, dtype=np.uint32)
+    ids = np.stack([(p >> (8 * k)) & 0xFF for k in range(3)], axis=1).astype(np.int64)
+    used = np.stack([(p >> (24 + k)) & 1 for k in range(3)], axis=1).astype(bool)
+    return piece_planes()[np.where(used, 37, ids)]
+
+
+def expand_mask(mask_planes_u64):
+    m = np.ascontiguousarray(np.asarray(mask_planes_u64, dtype=np.uint64).T)      # [N,3]
+    return np.unpackbits(m.view(np.uint8).reshape(-1, 24), axis=1, bitorder="little").astype(np.int8)
+
+
+class LazyObs(dict):
+    """Observation dict whose dense arrays are expanded from the packed host copy on first
+    access (keys and layouts of wrappers.py:118-126)."""
+
+    def __init__(self, board, pieces, mask):
+        super().__init__()
+        self.packed = dict(board=board, pieces=pieces, mask=mask)
+
+    def __missing__(self, key):
+        if key == "board":
+            v = expand_board(self.packed["board"])
+        elif key == "pieces":
+            v = expand_pieces(self.packed["pieces"])
+        elif key == "action_mask":
+            v = expand_mask(self.packed["mask"])
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def keys(self):
+        return ["board", "pieces", "action_mask"]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return 3
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def __contains__(self, k):
+        return k in ("board", "pieces", "action_mask")
+
+
+class LazyInfos:
+    """Sequence of per-env info dicts (block_blast_env.py:266-288) built on demand.
+
+    The training loop only reads ``final_score``/``score`` and ``moves`` of terminated envs
+    (scripts/train.py:196-201); those come from the step's own outputs.  The other fields are
+    read from the env state when first asked for (one device->host state copy)."""
+
+    def __init__(self, venv, terminated, invalid, ep_score, ep_len):
+        self._venv, self._term, self._inv = venv, terminated, invalid
+        self._eps, self._epl = ep_score, ep_len
+        self._state = None
+
+    def __len__(self):
+        return len(self._term)
+
+    def _rec(self):
+        if self._state is None:
+            self._state = self._venv._handle.get_state()
+        return self._state
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if bool(self._term[i]):
+            # stats of the finished episode; the env has already been reset
+            return {"score": int(self._eps[i]), "final_score": int(self._eps[i]), "moves": int(self._epl[i]),
+                    "invalid_action": False}
+        s = self._rec()[i]
+        board = int(s["board"])
+        return {"score": int(s["score"]), "moves": int(s["moves"]), "lines_cleared": int(s["lines_total"]),
+                "max_combo": int(s["max_streak"]), "blocks_placed": int(s["blocks_total"]),
+                "board_fill": bin(board).count("1") / 64, "holes": int(s["aux"] & 0xFF),
+                "invalid_action": bool(self._inv[i]) if self._inv is not None else False}
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class VectorizedBlockBlastEnv:
+    """Batched Block Blast env on one GPU (reference: wrappers.py:14-141).
+
+    Extra keyword-only arguments (not in the reference): ``output`` (see module docstring),
+    ``global_env_offset`` (id of env 0 of this shard — trajectories depend on
+    ``(seed, global id, actions)`` only, so shards over several GPUs reproduce the one-GPU
+    run), ``reseed_on_reset`` (the reference re-seeds env i with ``seed+i`` on EVERY reset when
+    a seed is given, so each episode replays the same trio stream; default False = the stream
+    continues, True = that behaviour)."""
+
+    def __init__(self, num_envs, seed=None, reward_config=None, *, output="numpy",
+                 global_env_offset=0, reseed_on_reset=False):
+        import torch
+        assert output in ("numpy", "torch", "packed")
+        self.num_envs = int(num_envs)
+        self.reward_config = reward_config
+        self.output = output
+        self.global_env_offset = int(global_env_offset)
+        self.reseed_on_reset = bool(reseed_on_reset)
+        self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        self.observation_space, self.action_space = _spaces()
+        self.single_action_space = self.action_space
+        self._torch = torch
+        self._make_handle()
+        n, dev = self.num_envs, self._handle.device
+        # device-resident step outputs (reused every step)
+        self._d_actions = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._d_rewards = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._d_term = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._d_mask = torch.zeros((3, n), dtype=torch.int64, device=dev)
+        self._d_board = torch.zeros(n, dtype=torch.int64, device=dev)
+        self._d_pieces = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._d_ep_score = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._d_ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._d_info = torch.zeros(n, dtype=torch.int32, device=dev)
+        if output == "numpy":
+            pin = dict(pin_memory=True)
+            self._h_actions = torch.zeros(n, dtype=torch.int32, **pin)
+            self._h_rewards = torch.zeros(n, dtype=torch.float32, **pin)
+            self._h_term = torch.zeros(n, dtype=torch.uint8, **pin)
+            self._h_board = torch.zeros(n, dtype=torch.int64, **pin)
+            self._h_pieces = torch.zeros(n, dtype=torch.int32, **pin)
+            self._h_mask = torch.zeros((3, n), dtype=torch.int64, **pin)
+            self._h_ep_score = torch.zeros(n, dtype=torch.int32, **pin)
+            self._h_ep_len = torch.zeros(n, dtype=torch.int32, **pin)
+        self._dones = np.zeros(n, dtype=bool)
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_handle(self):
+        flags = capi.ENV_RESEED_ON_RESET if self.reseed_on_reset else 0
+        self._handle = capi.EnvHandle(self.num_envs, self.seed, self.global_env_offset, self.reward_config, flags)
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def _obs_device(self):
+        """obs of the current states in the selected device format."""
+        torch = self._torch
+        self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
+        if self.output == "packed":
+            return {"board": self._d_board, "pieces": self._d_pieces, "mask": self._d_mask}
+        n = self.num_envs
+        obs = torch.empty((n, 4, 8, 8), dtype=torch.float32, device=self._d_board.device)
+        dense = torch.empty((n, ACTION_SPACE_SIZE), dtype=torch.uint8, device=self._d_board.device)
+        capi.unpack_obs(self._d_board, self._d_pieces, self._d_mask, n, obs=obs, mask_dense=dense)
+        return {"board": obs[:, 0], "pieces": obs[:, 1:], "action_mask": dense.view(torch.int8), "nchw": obs}
+
+    def _obs_numpy(self):
+        t = self._torch
+        self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
+        self._h_board.copy_(self._d_board, non_blocking=True)
+        self._h_pieces.copy_(self._d_pieces, non_blocking=True)
+        self._h_mask.copy_(self._d_mask, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return LazyObs(self._h_board.numpy().view(np.uint64).copy(), self._h_pieces.numpy().view(np.uint32).copy(),
+                       self._h_mask.numpy().view(np.uint64).copy())
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self, seed=None):
+        """wrappers.py:53-73.  A non-None seed re-creates the Philox streams with it."""
+        if seed is not None:
+            self._handle.close()
+            self.seed = int(seed)
+            self._make_handle()     # deals once, like constructing the reference envs
+        self._handle.reset()
+        self._dones.fill(False)
+        obs = self._obs_numpy() if self.output == "numpy" else self._obs_device()
+        return obs, LazyInfos(self, np.zeros(self.num_envs, bool), None, None, None)
+
+    def step(self, actions):
+        """wrappers.py:75-116: returns (obs, rewards, terminated, truncated, infos)."""
+        torch = self._torch
+        n = self.num_envs
+        if self.output == "numpy":
+            a = np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions).reshape(-1)
+            assert a.shape[0] == n, "expected %d actions" % n
+            self._h_actions.numpy()[:] = a          # int cast like int(action) in wrappers.py:94
+            self._handle.step_host(self._h_actions, self._h_rewards, self._h_term, self._h_board, self._h_pieces,
+                                   self._h_mask, self._h_ep_score, self._h_ep_len)
+            rewards = self._h_rewards.numpy().copy()
+            term = self._h_term.numpy().astype(bool)
+            obs = LazyObs(self._h_board.numpy().view(np.uint64).copy(), self._h_pieces.numpy().view(np.uint32).copy(),
+                          self._h_mask.numpy().view(np.uint64).copy())
+            infos = LazyInfos(self, term, None, self._h_ep_score.numpy().copy(), self._h_ep_len.numpy().copy())
+            return obs, rewards, term, np.zeros(n, dtype=bool), infos
+        if isinstance(actions, torch.Tensor):
+            self._d_actions.copy_(actions.reshape(-1), non_blocking=True)
+        else:
+            self._d_actions.copy_(torch.as_tensor(np.asarray(actions).reshape(-1).astype(np.int32)))
+        self._handle.step(self._d_actions, self._d_rewards, self._d_term, self._d_mask, self._d_ep_score,
+                          self._d_ep_len, self._d_info)
+        obs = self._obs_device()
+        term = self._d_term.bool()
+        infos = {"ep_score": self._d_ep_score, "ep_len": self._d_ep_len, "info": self._d_info}
+        return obs, self._d_rewards, term, torch.zeros_like(term), infos
+
+    def get_action_masks(self):
+        """wrappers.py:128-131: bool [N,192]."""
+        torch = self._torch
+        self._handle.observe(None, None, self._d_mask)
+        dense = torch.empty((self.num_envs, ACTION_SPACE_SIZE), dtype=torch.uint8, device=self._d_mask.device)
+        capi.unpack_obs(None, None, self._d_mask, self.num_envs, obs=None, mask_dense=dense, n=self.num_envs)
+        if self.output == "numpy":
+            return dense.cpu().numpy().astype(bool)
+        return dense.bool()
+
+    def sample_valid_actions(self):
+        """wrappers.py:133-136: a uniformly random valid action per env (0 if none).  The
+        draw uses torch's CUDA generator, not numpy's global RNG."""
+        torch = self._torch
+        self._handle.observe(None, None, self._d_mask)
+        logits = torch.zeros((self.num_envs, ACTION_SPACE_SIZE), dtype=torch.float32, device=self._d_mask.device)
+        self._sample_ctr = getattr(self, "_sample_ctr", 0) + 1
+        capi.masked_sample(logits, self._d_mask, self.num_envs, self.seed ^ 0x5DEECE66D, self._sample_ctr, 0,
+                           self._d_actions)
+        if self.output == "numpy":
+            return self._d_actions.cpu().numpy().astype(np.int64)
+        return self._d_actions.clone()
+
+    def close(self):
+        self._handle.close()
+
+
+class BlockBlastEnv:
+    """Single environment with the reference's semantics (block_blast_env.py:20-323): no
+    auto-reset — after game over every action is rejected with reward -10 until ``reset``.
+    A view over a 1-env ``bb_env``; meant for evaluation / play, not throughput."""
+
+    metadata = {"render_modes": ["human", "ansi"]}
+    BOARD_SIZE = BOARD_SIZE
+    NUM_PIECES_PER_TURN = NUM_PIECES_PER_TURN
+    ACTION_SPACE_SIZE = ACTION_SPACE_SIZE
+
+    def __init__(self, render_mode=None, reward_config=None, seed=None):
+        import torch
+        self._torch = torch
+        self.render_mode = render_mode
+        self.seed_value = seed
+        self.reward_config = dict(capi.REWARD_DEFAULTS)
+        if reward_config:
+            self.reward_config.update(reward_config)
+        self.observation_space, self.action_space = _spaces()
+        self._open(seed)
+
+    def _open(self, seed):
+        torch = self._torch
+        s = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        flags = capi.ENV_NO_AUTO_RESET | (capi.ENV_RESEED_ON_RESET if seed is not None else 0)
+        self._h = capi.EnvHandle(1, s, 0, self.reward_config, flags)
+        dev = self._h.device
+        self._a = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._r = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._t = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self._m = torch.zeros((3, 1), dtype=torch.int64, device=dev)
+        self._i = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _action_to_move(self, action):
+        return action // 64, (action % 64) // 8, action % 8
+
+    def _move_to_action(self, piece_idx, row, col):
+        return piece_idx * 64 + row * 8 + col
+
+    def _state(self):
+        return self._h.get_state()[0]
+
+    def _get_observation(self):
+        s = self._state()
+        self._h.observe(None, None, self._m)
+        m = self._m.cpu().numpy().view(np.uint64)
+        return {"board": expand_board(np.array([s["board"]]))[0], "pieces": expand_pieces(np.array([s["pieces"]]))[0],
+                "action_mask": expand_mask(m)[0]}
+
+    def _get_info(self, info_word=None):
+        s = self._state()
+        info = {"score": int(s["score"]), "moves": int(s["moves"]), "lines_cleared": int(s["lines_total"]),
+                "max_combo": int(s["max_streak"]), "blocks_placed": int(s["blocks_total"]),
+                "board_fill": bin(int(s["board"])).count("1") / 64, "holes": _holes(int(s["board"])),
+                "invalid_action": False}
+        if info_word is not None:
+            info["last_move"] = {"blocks_placed": (info_word >> 4) & 0xF, "lines_cleared": (info_word >> 1) & 7,
+                                 "combo_multiplier": (info_word >> 8) & 7}
+        return info
+
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.seed_value = seed
+            self._h.close()
+            self._open(seed)
+        self._h.reset()
+        return self._get_observation(), self._get_info()
+
+    def step(self, action):
+        self._a.fill_(int(action))
+        self._h.step(self._a, self._r, self._t, None, None, None, self._i)
+        word = int(self._i.item())
+        reward = float(self._r.item())
+        terminated = bool(self._t.item())
+        if word & 1:
+            info = self._get_info()
+            info["invalid_action"] = True
+            return self._get_observation(), -10.0, False, False, info
+        return self._get_observation(), reward, terminated, False, self._get_info(word)
+
+    def get_action_mask(self):
+        return self._get_observation()["action_mask"].astype(bool)
+
+    def get_valid_actions(self):
+        return np.where(self.get_action_mask())[0].tolist()
+
+    def sample_valid_action(self):
+        va = self.get_valid_actions()
+        return int(np.random.choice(va)) if va else 0
+
+    def render(self):
+        return None
+
+    def close(self):
+        self._h.close()
+
+
+def _holes(board):
+    """Host-side restatement used only for the single-env info dict of a game-over state
+    (aux carries the post-move value for live states)."""
+    k = 0
+    for r in range(8):
+        for c in range(8):
+            if (board >> (r * 8 + c)) & 1:
+                continue
+            ok = True
+            for dr, dc in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                rr, cc = r + dr, c + dc
+                if 0 <= rr < 8 and 0 <= cc < 8 and not (board >> (rr * 8 + cc)) & 1:
+                    ok = False
+            k += ok
+    return k

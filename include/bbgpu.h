@@ -1,0 +1,158 @@
+/* bbgpu.h — C ABI of libbbgpu.so: B200 (sm_100a) batched Block Blast simulator and the
+ * masked-PPO rollout kernels.
+ *
+ * The reference (rfahd1525/Block-Blast-AI---Reinforcement-Learning-Agent) is pure Python and
+ * has no FFI; its boundary for this path is the Python class API.  Each entry point below
+ * names the reference interface it replaces (file:line in the reference checkout); the
+ * Python mirror of those classes lives in block-blast-ai---reinforcement-learning-agent_b200/
+ * and INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; bb_last_error() gives the message of
+ *     the last failure on the calling thread.  No exceptions, no aborts.
+ *   - pointers documented "device" are CUDA device pointers owned by the caller (e.g. torch
+ *     tensors); the library never frees or retains them after the call returns.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     calls are asynchronous on it, never synchronise, and never allocate after create
+ *     (except the *_host entry points, which copy and synchronise).
+ *   - a bb_env lives on the CUDA device current at bb_env_create time; it is not thread-safe.
+ *   - bit convention for boards and masks: bit = row*8 + col; action = piece*64 + row*8 + col
+ *     (src/environment/block_blast_env.py:104-132).
+ *   - action masks are three bit-planes per env stored plane-major: mask[p*n_envs + i].
+ *   - packed pieces word: bytes 0..2 = piece indices (PIECE_LIST order,
+ *     src/game/pieces.py:244-318), byte 3 = used bits (bit p set = piece p already placed).
+ *   - invalid actions are NOT errors: reward -10, state untouched (block_blast_env.py:240-245).
+ */
+#ifndef BBGPU_H
+#define BBGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+/* flags for bb_env_create */
+#define BB_ENV_RESEED_ON_RESET 1u /* every reset restarts the env's trio stream: the reference's
+                                     behaviour when a seed is given (wrappers.py:102 ->
+                                     block_blast_env.py:215 -> engine.py:137-138) */
+#define BB_ENV_NO_AUTO_RESET 2u   /* single-env semantics (BlockBlastEnv.step): stay GAME_OVER */
+
+/* dtype codes for dense outputs */
+#define BB_F32 0
+#define BB_BF16 1
+#define BB_U8 2
+
+typedef struct bb_env bb_env;
+
+int bb_version(void);
+const char* bb_last_error(void);
+
+/* The 37-piece tables compiled into the kernels, for cross-checking against
+ * src/game/pieces.py:78-318.  Host pointers; any may be NULL. */
+int bb_piece_table(uint64_t* masks37, uint64_t* inb37, uint8_t* nblk37);
+
+/* VectorizedBlockBlastEnv.__init__ (src/environment/wrappers.py:21-50) + the first reset.
+ * reward_cfg = {line_clear_base, block_placed, game_over_penalty, hole_penalty, center_bonus,
+ * combo_multiplier_bonus, survival_bonus} (block_blast_env.py:63-71); NULL = defaults.
+ * Env i draws candidate trios from Philox stream (seed, global_env_offset + i), so a shard on
+ * any GPU reproduces the same trajectories as the single-GPU run. */
+int bb_env_create(bb_env** out, int64_t n_envs, uint64_t seed, int64_t global_env_offset,
+                  const double reward_cfg[7], uint32_t flags);
+int bb_env_destroy(bb_env* env);
+int64_t bb_env_num_envs(const bb_env* env);
+
+/* VectorizedBlockBlastEnv.reset (wrappers.py:53-73).  reset_mask: device u8[n] or NULL (= all).
+ * mask_out: device u64[3*n] or NULL. */
+int bb_env_reset(bb_env* env, const uint8_t* reset_mask, uint64_t* mask_out, void* stream);
+
+/* VectorizedBlockBlastEnv.step (wrappers.py:75-116): BlockBlastEnv.step
+ * (block_blast_env.py:224-264) -> GameEngine.make_move (src/game/engine.py:390-454) with
+ * auto-reset.  One fused kernel: validate, place, clear rows/cols, score+streak, trio
+ * regeneration (Philox + the "all three placeable" search, engine.py:155-238), game over,
+ * shaped reward (block_blast_env.py:148-193), auto-reset, next action mask.
+ *   actions     device i32[n]
+ *   rewards     device f32[n]
+ *   terminated  device u8[n]
+ *   mask_out    device u64[3*n]   action mask of the state after the step     (may be NULL)
+ *   ep_score    device i32[n]     written only where terminated: info['final_score'] (NULL ok)
+ *   ep_len      device i32[n]     written only where terminated: info['moves']       (NULL ok)
+ *   info_out    device u32[n]     bit0 invalid_action, bits1-3 lines_cleared, bits4-7
+ *                                 blocks_placed, bits8-10 combo_multiplier, bits11-17 candidate
+ *                                 trios drawn                                    (NULL ok)
+ */
+int bb_env_step(bb_env* env, const int32_t* actions, float* rewards, uint8_t* terminated,
+                uint64_t* mask_out, int32_t* ep_score, int32_t* ep_len, uint32_t* info_out,
+                void* stream);
+
+/* n_steps of the same step with the uniform-random-valid-action policy of
+ * sample_valid_actions (wrappers.py:133-136, block_blast_env.py:318-323) fused in: the action
+ * is the k-th set bit of the 192-bit mask, k = mulhi(philox_word, n_valid).  State stays in
+ * registers across the n_steps.  Outputs (all may be NULL) describe the LAST step;
+ * stats: device u64[4] accumulated with atomics: env-steps, episodes, sum of final scores,
+ * sum of episode lengths. */
+int bb_env_step_random(bb_env* env, int32_t n_steps, int32_t* actions_out, float* rewards,
+                       uint8_t* terminated, uint64_t* mask_out, uint64_t* stats, void* stream);
+
+/* Packed observation of the current states (engine.get_observation, engine.py:478-507):
+ * board_out device u64[n], pieces_out device u32[n], mask_out device u64[3*n]; any NULL. */
+int bb_env_observe(bb_env* env, uint64_t* board_out, uint32_t* pieces_out, uint64_t* mask_out,
+                   void* stream);
+
+/* Full state export / import for checkpoints and parity tests (GameEngine.get_state /
+ * set_state, engine.py:456-476, plus counters).  HOST arrays of n_envs records, 48 bytes each:
+ * {u64 board; u32 pieces; u32 aux(prev_holes | prev_center_filled<<8 | game_over<<16);
+ *  i32 score, streak, moves, lines_total, max_streak, blocks_total; u32 draw_ctr, policy_ctr}.
+ * Synchronises the stream. */
+int bb_env_get_state(bb_env* env, void* host_records, void* stream);
+int bb_env_set_state(bb_env* env, const void* host_records, void* stream);
+
+/* Same as bb_env_step but with HOST buffers (pinned memory recommended): copies actions to
+ * the device, steps, copies rewards/terminated/packed obs back, synchronises.  This is the
+ * call the numpy-facing VectorizedBlockBlastEnv.step makes.  board/pieces/mask/ep_* may be
+ * NULL to skip that copy. */
+int bb_env_step_host(bb_env* env, const int32_t* h_actions, float* h_rewards,
+                     uint8_t* h_terminated, uint64_t* h_board, uint32_t* h_pieces,
+                     uint64_t* h_mask, int32_t* h_ep_score, int32_t* h_ep_len, void* stream);
+
+/* Observation expansion (engine.get_observation + Piece.to_mask, engine.py:489-507,
+ * src/game/pieces.py:39-45; network input cat([board, pieces]), src/models/network.py:152-158).
+ *   board device u64[n], pieces device u32[n], mask device u64[3*n] plane-major with plane
+ *   stride mask_stride (elements)
+ *   obs_nchw    device [n,4,8,8] of obs_dtype (BB_F32 / BB_BF16); NULL to skip
+ *   mask_dense  device [n,192] of mask_dtype (BB_U8 / BB_F32);  NULL to skip */
+int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask,
+                  int64_t mask_stride, void* obs_nchw, int obs_dtype, void* mask_dense,
+                  int mask_dtype, int64_t n, void* stream);
+
+/* Masked categorical head (BlockBlastNetwork.forward masking + get_action_and_value +
+ * _masked_entropy, src/models/network.py:172-262) fused in one kernel.
+ *   logits  device [n,192] of logits_dtype (BB_F32 / BB_BF16), raw (unmasked)
+ *   mask    device u64[3*n] plane-major, plane stride mask_stride
+ *   mode 0: sample  action ~ softmax(masked logits) by inverse CDF on a Philox uniform
+ *                   (SAMPLE stream: key seed, counter (row, call_counter))
+ *   mode 1: argmax  (deterministic=True)
+ *   mode 2: evaluate the actions given in `action` (PPO update path)
+ *   action   device i32[n]  (out for modes 0/1, in for mode 2)
+ *   logp     device f32[n]  log(clamp(p/sum(p), eps, 1-eps))[action]  (torch Categorical)
+ *   entropy  device f32[n]  masked entropy (network.py:232-262); NULL to skip */
+int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
+                     int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
+                     int32_t* action, float* logp, float* entropy, int64_t n, void* stream);
+
+/* GAE and returns (RolloutBuffer.compute_returns_and_advantages, src/agents/ppo.py:141-169),
+ * reverse scan over T, float32, same operation order as the reference (bit-identical).
+ *   rewards, values, dones: device f32[T*N] time-major; last_values device f32[N]
+ *   adv, ret: device f32[T*N]
+ *   moments: device f64[2] or NULL: += sum(adv), sum(adv^2)  (whole-buffer normalisation,
+ *   ppo.py:196; all-reduce them across ranks) */
+int bb_gae(const float* rewards, const float* values, const float* dones,
+           const float* last_values, double gamma, double lam, float* adv, float* ret,
+           double* moments, int64_t T, int64_t N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBGPU_H */

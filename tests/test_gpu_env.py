@@ -1,0 +1,265 @@
+"""GPU parity tests for K1 (fused env step) through the C ABI, against the oracle and the
+golden traces recorded from the reference.  Bit-exact: boards, 3x64-bit masks, float32 reward
+bit patterns, done flags, scores, episode stats, candidate-trio consumption."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def _dev_buffers(torch, n):
+    dev = "cuda"
+    return dict(actions=torch.zeros(n, dtype=torch.int32, device=dev), rewards=torch.zeros(n, dtype=torch.float32, device=dev),
+                term=torch.zeros(n, dtype=torch.uint8, device=dev), mask=torch.zeros((3, n), dtype=torch.int64, device=dev),
+                ep_score=torch.full((n,), -1, dtype=torch.int32, device=dev), ep_len=torch.full((n,), -1, dtype=torch.int32, device=dev),
+                info=torch.zeros(n, dtype=torch.int32, device=dev), board=torch.zeros(n, dtype=torch.int64, device=dev),
+                pieces=torch.zeros(n, dtype=torch.int32, device=dev))
+
+
+def _gpu_step(torch, h, B, actions):
+    B["actions"].copy_(torch.from_numpy(np.ascontiguousarray(actions, np.int32)))
+    B["ep_score"].fill_(-1)
+    B["ep_len"].fill_(-1)
+    h.step(B["actions"], B["rewards"], B["term"], B["mask"], B["ep_score"], B["ep_len"], B["info"])
+    h.observe(B["board"], B["pieces"], None)
+    torch.cuda.synchronize()
+    return dict(rewards=B["rewards"].cpu().numpy(), terminated=B["term"].cpu().numpy(),
+                mask=B["mask"].cpu().numpy().view(np.uint64).T.copy(), ep_score=B["ep_score"].cpu().numpy(),
+                ep_len=B["ep_len"].cpu().numpy(), info=B["info"].cpu().numpy().view(np.uint32),
+                board=B["board"].cpu().numpy().view(np.uint64), pieces=B["pieces"].cpu().numpy().view(np.uint32))
+
+
+def _pieces4(p):
+    return np.stack([p & 0xFF, (p >> 8) & 0xFF, (p >> 16) & 0xFF, (p >> 24) & 0xFF], axis=1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name", ["vec_trace.npz", "vec_trace_cfg.npz"])
+def test_gpu_replays_reference_golden_trace(torch, name):
+    """config 2 of BASELINE.json: fixed piece/action sequence, bit-exact vs the reference."""
+    from bbgpu import capi
+    tr = np.load(os.path.join(G, name))
+    cfg = json.loads(str(tr["reward_cfg_json"]))
+    n = tr["actions"].shape[1]
+    h = capi.EnvHandle(n, int(tr["seed"]), 0, cfg)
+    B = _dev_buffers(torch, n)
+    h.observe(B["board"], B["pieces"], B["mask"])
+    torch.cuda.synchronize()
+    assert np.array_equal(B["board"].cpu().numpy().view(np.uint64), tr["board0"])
+    assert np.array_equal(_pieces4(B["pieces"].cpu().numpy().view(np.uint32)), tr["pieces0"])
+    assert np.array_equal(B["mask"].cpu().numpy().view(np.uint64).T, tr["mask0"])
+    for t in range(tr["actions"].shape[0]):
+        o = _gpu_step(torch, h, B, tr["actions"][t])
+        assert np.array_equal(o["board"], tr["board"][t]), t
+        assert np.array_equal(_pieces4(o["pieces"]), tr["pieces"][t]), t
+        assert np.array_equal(o["mask"], tr["mask"][t]), t
+        assert np.array_equal(o["rewards"].view(np.uint32), tr["rewards"][t].view(np.uint32)), t
+        assert np.array_equal(o["terminated"].astype(bool), tr["terminated"][t]), t
+        assert np.array_equal((o["info"] & 1).astype(bool), tr["invalid"][t]), t
+        tt = tr["terminated"][t]
+        assert np.array_equal(o["ep_score"][tt], tr["ep_score"][t][tt]), t
+        assert np.array_equal(o["ep_len"][tt], tr["ep_len"][t][tt]), t
+        if t % 250 == 0 or t == tr["actions"].shape[0] - 1:
+            st = h.get_state()
+            assert np.array_equal(st["score"], tr["score"][t]) and np.array_equal(st["streak"], tr["streak"][t])
+            assert np.array_equal(st["moves"], tr["moves"][t]) and np.array_equal(st["lines_total"], tr["lines_total"][t])
+            assert np.array_equal(st["max_streak"], tr["max_streak"][t]) and np.array_equal(st["blocks_total"], tr["blocks_total"][t])
+            assert np.array_equal(st["draw_ctr"], tr["draws"][t])
+            assert np.array_equal(st["aux"] & 0xFF, tr["holes"][t])
+    h.close()
+
+
+@pytest.mark.parametrize("reseed", [False, True])
+def test_gpu_vs_c_oracle_many_envs(torch, reseed):
+    from bbgpu import capi, philox
+    from oracle import bb_oracle_c as OC
+    n, T, seed, off = 4096, 120, 1234, 1000
+    streams = philox.candidate_trios(seed, off + np.arange(n), 512)
+    ora = OC.CVecEnv(streams, reseed=reseed, n_threads=8)
+    h = capi.EnvHandle(n, seed, off, None, capi.ENV_RESEED_ON_RESET if reseed else 0)
+    B = _dev_buffers(torch, n)
+    rs = np.random.RandomState(0)
+    _, _, m = ora.export()
+    n_term = 0
+    for t in range(T):
+        # uniformly random valid action per env from the oracle's mask, ~2% garbage actions
+        bits = np.unpackbits(m.view(np.uint8).reshape(n, 24), axis=1, bitorder="little")
+        r = rs.rand(n, 192) * bits
+        acts = r.argmax(axis=1).astype(np.int32)
+        bad = rs.rand(n) < 0.02
+        acts[bad] = rs.randint(-100, 300, bad.sum())
+        oo = ora.step(acts)
+        go = _gpu_step(torch, h, B, acts)
+        assert np.array_equal(oo["board"], go["board"]), t
+        assert np.array_equal(oo["pieces"], _pieces4(go["pieces"])), t
+        assert np.array_equal(oo["mask"], go["mask"]), t
+        assert np.array_equal(oo["rewards"].view(np.uint32), go["rewards"].view(np.uint32)), t
+        assert np.array_equal(oo["terminated"], go["terminated"]), t
+        assert np.array_equal(oo["invalid"], (go["info"] & 1).astype(np.uint8)), t
+        tt = oo["terminated"].astype(bool)
+        n_term += tt.sum()
+        assert np.array_equal(oo["ep_score"][tt], go["ep_score"][tt]) and np.array_equal(oo["ep_len"][tt], go["ep_len"][tt])
+        m = oo["mask"]
+    st, os_ = h.get_state(), ora.stats()
+    assert np.array_equal(st["score"], os_[:, 0]) and np.array_equal(st["moves"], os_[:, 2])
+    if not reseed:
+        assert np.array_equal(st["draw_ctr"], os_[:, 7])
+    assert n_term > 1000 and not ora.exhausted()
+    h.close()
+
+
+def test_fused_random_policy_parity_and_multistep_equivalence(torch):
+    from bbgpu import capi, philox
+    from oracle import bb_oracle_c as OC
+    n, T, seed = 1024, 96, 77
+    streams = philox.candidate_trios(seed, np.arange(n), 512)
+    ora = OC.CVecEnv(streams, n_threads=8)
+    words = philox.policy_words(seed, np.arange(n), np.arange(T))
+    h1 = capi.EnvHandle(n, seed)
+    h2 = capi.EnvHandle(n, seed)
+    B = _dev_buffers(torch, n)
+    stats1 = torch.zeros(4, dtype=torch.int64, device="cuda")
+    stats2 = torch.zeros(4, dtype=torch.int64, device="cuda")
+    eps = score = length = 0
+    for t in range(T):
+        _, _, m = ora.export()
+        bits = np.unpackbits(m.view(np.uint8).reshape(n, 24), axis=1, bitorder="little").astype(np.int64)
+        nv = bits.sum(1)
+        k = philox.mulhi32(words[t], nv).astype(np.int64)
+        csum = np.cumsum(bits, axis=1)
+        acts = (csum <= k[:, None]).sum(axis=1).astype(np.int32)   # index of the (k+1)-th set bit
+        h1.step_random(1, B["actions"], B["rewards"], B["term"], B["mask"], stats1)
+        torch.cuda.synchronize()
+        assert np.array_equal(B["actions"].cpu().numpy(), acts), t
+        oo = ora.step(acts)
+        assert np.array_equal(oo["rewards"].view(np.uint32), B["rewards"].cpu().numpy().view(np.uint32)), t
+        assert np.array_equal(oo["terminated"], B["term"].cpu().numpy()), t
+        assert np.array_equal(oo["mask"], B["mask"].cpu().numpy().view(np.uint64).T), t
+        tt = oo["terminated"].astype(bool)
+        eps += tt.sum(); score += oo["ep_score"][tt].sum(); length += oo["ep_len"][tt].sum()
+    h2.step_random(T, None, None, None, None, stats2)      # one launch, state in registers
+    torch.cuda.synchronize()
+    s1, s2 = h1.get_state(), h2.get_state()
+    assert s1.tobytes() == s2.tobytes()
+    assert stats1.cpu().tolist() == stats2.cpu().tolist() == [n * T, int(eps), int(score), int(length)]
+    h1.close(); h2.close()
+
+
+def test_shards_reproduce_the_single_device_run(torch):
+    """trajectories depend on (seed, global env id, actions) only."""
+    from bbgpu import capi
+    n, seed, T = 2048, 5, 200
+    whole = capi.EnvHandle(n, seed, 0)
+    lo = capi.EnvHandle(n // 2, seed, 0)
+    hi = capi.EnvHandle(n // 2, seed, n // 2)
+    for h in (whole, lo, hi):
+        h.step_random(T)
+    torch.cuda.synchronize()
+    w = whole.get_state()
+    # policy_ctr/draw_ctr are per env, so the records must match field for field
+    assert w[: n // 2].tobytes() == lo.get_state().tobytes()
+    assert w[n // 2:].tobytes() == hi.get_state().tobytes()
+    for h in (whole, lo, hi):
+        h.close()
+
+
+def test_state_roundtrip_and_host_step_equals_device_step(torch):
+    from bbgpu import capi
+    n, seed = 1000, 3          # deliberately not a multiple of the block size
+    a = capi.EnvHandle(n, seed)
+    a.step_random(37)
+    rec = a.get_state()
+    b = capi.EnvHandle(n, 999)
+    b.set_state(rec)
+    assert b.get_state().tobytes() == rec.tobytes()
+    b.close()
+    b = capi.EnvHandle(n, seed)     # same seed: same Philox streams from the restored counters
+    b.set_state(rec)
+    B = _dev_buffers(torch, n)
+    a.observe(None, None, B["mask"])
+    torch.cuda.synchronize()
+    m = B["mask"].cpu().numpy().view(np.uint64).T
+    bits = np.unpackbits(np.ascontiguousarray(m).view(np.uint8).reshape(n, 24), axis=1, bitorder="little")
+    acts = (np.random.RandomState(0).rand(n, 192) * bits).argmax(1).astype(np.int32)
+    go = _gpu_step(torch, a, B, acts)
+    pin = lambda dt, shape=(n,): torch.zeros(shape, dtype=dt).pin_memory()
+    ha, hr, ht = pin(torch.int32), pin(torch.float32), pin(torch.uint8)
+    hb, hp, hm, hs, hl = pin(torch.int64), pin(torch.int32), pin(torch.int64, (3, n)), pin(torch.int32), pin(torch.int32)
+    ha.numpy()[:] = acts
+    b.step_host(ha, hr, ht, hb, hp, hm, hs, hl)
+    assert np.array_equal(hr.numpy().view(np.uint32), go["rewards"].view(np.uint32))
+    assert np.array_equal(ht.numpy(), go["terminated"])
+    assert np.array_equal(hb.numpy().view(np.uint64), go["board"])
+    assert np.array_equal(hp.numpy().view(np.uint32), go["pieces"])
+    assert np.array_equal(hm.numpy().view(np.uint64).T, go["mask"])
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+    a.close(); b.close()
+
+
+def test_no_auto_reset_single_env_semantics(torch):
+    """BlockBlastEnv (no wrapper): after game over every action is rejected with -10."""
+    from bbgpu import capi
+    n = 256
+    h = capi.EnvHandle(n, 11, 0, None, capi.ENV_NO_AUTO_RESET)
+    B = _dev_buffers(torch, n)
+    done = np.zeros(n, bool)
+    for t in range(120):
+        h.step_random(1, B["actions"], B["rewards"], B["term"], B["mask"], None)
+        torch.cuda.synchronize()
+        r, tm = B["rewards"].cpu().numpy(), B["term"].cpu().numpy().astype(bool)
+        assert (r[done] == -10.0).all() and not tm[done].any()
+        assert (B["mask"].cpu().numpy()[:, done] == 0).all()
+        done |= tm
+    assert done.sum() > n // 2
+    st = h.get_state()
+    assert ((st["aux"] >> 16) & 1).astype(bool).tolist() == done.tolist()
+    h.close()
+
+
+def test_full_size_properties_262144_envs(torch):
+    """BASELINE config 3 size: invariants that need no oracle."""
+    from bbgpu import capi
+    import hostrules as H
+    n, T = 262144, 60
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    h = capi.EnvHandle(n, 42)
+    for _ in range(T):
+        h.step_random(1, None, None, None, None, stats)
+    torch.cuda.synchronize()
+    s = stats.cpu().tolist()
+    assert s[0] == n * T and s[1] > 0
+    mean_len = s[3] / s[1]
+    assert 8 < mean_len < 25, mean_len          # random play: ~14.7 moves per episode
+    st = h.get_state()
+    b = st["board"]
+    # no full row / column survives a step
+    rows = b.view(np.uint8).reshape(n, 8)
+    assert not (rows == 0xFF).any()
+    cols = np.bitwise_and.reduce(rows, axis=1)
+    assert not cols.any()
+    # stored holes / center counters equal a recomputation
+    L = H.lib()
+    idx = np.random.RandomState(0).choice(n, 2000, replace=False)
+    for i in idx:
+        assert L.bbh_holes(int(b[i])) == int(st["aux"][i] & 0xFF)
+        assert L.bbh_center(int(b[i])) == int((st["aux"][i] >> 8) & 0xFF)
+    # every env has a legal move (auto-reset) and unused pieces only
+    mask = torch.zeros((3, n), dtype=torch.int64, device="cuda")
+    h.observe(None, None, mask)
+    assert bool((mask != 0).any(dim=0).all())
+    # determinism: same seed, same trajectory
+    h2 = capi.EnvHandle(n, 42)
+    h2.step_random(T)
+    torch.cuda.synchronize()
+    assert h2.get_state().tobytes() == st.tobytes()
+    h.close(); h2.close()

@@ -1,0 +1,196 @@
+"""GPU parity tests for K2 (obs unpack), K3 (masked sample) and K4 (GAE)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+# ------------------------------------------------------------------ K4
+@pytest.mark.parametrize("T,N", [(128, 4096), (16, 8), (1, 3), (33, 1001), (128, 64), (7, 4)])
+def test_gae_bit_exact_with_oracle(torch, T, N):
+    from bbgpu import capi
+    from oracle import bb_oracle_c as OC
+    rs = np.random.RandomState(T * 1000 + N)
+    r = (rs.randn(T, N) * 2).astype(np.float32)
+    v = rs.randn(T, N).astype(np.float32)
+    d = (rs.rand(T, N) < 0.1).astype(np.float32)
+    lv = rs.randn(N).astype(np.float32)
+    want_a, want_r = OC.gae(r, v, d, lv, 0.99, 0.95)
+    tr, tv, td, tl = (torch.from_numpy(x).cuda() for x in (r, v, d, lv))
+    adv, ret = torch.empty_like(tr), torch.empty_like(tr)
+    mom = torch.zeros(2, dtype=torch.float64, device="cuda")
+    capi.gae(tr, tv, td, tl, 0.99, 0.95, adv, ret, mom)
+    torch.cuda.synchronize()
+    assert np.array_equal(adv.cpu().numpy().view(np.uint32), want_a.view(np.uint32))
+    assert np.array_equal(ret.cpu().numpy().view(np.uint32), want_r.view(np.uint32))
+    m = mom.cpu().numpy()
+    np.testing.assert_allclose(m[0], want_a.astype(np.float64).sum(), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(m[1], (want_a.astype(np.float64) ** 2).sum(), rtol=1e-9)
+
+
+def test_gae_matches_reference_golden(torch):
+    from bbgpu import capi
+    g = np.load(os.path.join(G, "gae_golden.npz"))
+    for tag in "abc":
+        tr, tv, td, tl = (torch.from_numpy(g[f"{tag}_{k}"]).cuda() for k in ("rewards", "values", "dones", "last"))
+        adv, ret = torch.empty_like(tr), torch.empty_like(tr)
+        capi.gae(tr, tv, td, tl, float(g["gamma"]), float(g["lam"]), adv, ret, None)
+        torch.cuda.synchronize()
+        # north_star tolerance is 1e-5 relative; the kernel is in fact bit-identical
+        np.testing.assert_allclose(adv.cpu().numpy(), g[f"{tag}_adv"], rtol=1e-5, atol=0)
+        assert np.array_equal(adv.cpu().numpy(), g[f"{tag}_adv"]) and np.array_equal(ret.cpu().numpy(), g[f"{tag}_ret"])
+
+
+# ------------------------------------------------------------------ K2
+def test_unpack_obs_matches_reference_layout(torch):
+    from bbgpu import capi, vec_env
+    n = 3000
+    h = capi.EnvHandle(n, 8)
+    h.step_random(25)
+    board = torch.zeros(n, dtype=torch.int64, device="cuda")
+    pieces = torch.zeros(n, dtype=torch.int32, device="cuda")
+    mask = torch.zeros((3, n), dtype=torch.int64, device="cuda")
+    h.observe(board, pieces, mask)
+    obs32 = torch.empty((n, 4, 8, 8), dtype=torch.float32, device="cuda")
+    obs16 = torch.empty((n, 4, 8, 8), dtype=torch.bfloat16, device="cuda")
+    m8 = torch.empty((n, 192), dtype=torch.uint8, device="cuda")
+    m32 = torch.empty((n, 192), dtype=torch.float32, device="cuda")
+    capi.unpack_obs(board, pieces, mask, n, obs=obs32, mask_dense=m8)
+    capi.unpack_obs(board, pieces, mask, n, obs=obs16, mask_dense=m32)
+    torch.cuda.synchronize()
+    b = board.cpu().numpy().view(np.uint64)
+    p = pieces.cpu().numpy().view(np.uint32)
+    m = mask.cpu().numpy().view(np.uint64)
+    want_board = vec_env.expand_board(b)
+    want_pieces = vec_env.expand_pieces(p)
+    want_mask = vec_env.expand_mask(m)
+    o = obs32.cpu().numpy()
+    assert np.array_equal(o[:, 0], want_board) and np.array_equal(o[:, 1:], want_pieces)
+    assert np.array_equal(obs16.float().cpu().numpy(), o)
+    assert np.array_equal(m8.cpu().numpy(), want_mask.astype(np.uint8))
+    assert np.array_equal(m32.cpu().numpy(), want_mask.astype(np.float32))
+    # cross-check the numpy expansion itself against the cell oracle on a few envs
+    from oracle import bb_oracle as O
+    for i in range(0, n, 211):
+        g = np.array(O.u64_to_grid(int(b[i])), dtype=np.float32)
+        assert np.array_equal(want_board[i], g)
+        for k in range(3):
+            pid, used = (int(p[i]) >> (8 * k)) & 0xFF, (int(p[i]) >> (24 + k)) & 1
+            plane = np.zeros((8, 8), np.float32)
+            if not used:
+                for dr, dc in O.PIECE_CELLS[pid]:
+                    plane[dr, dc] = 1
+            assert np.array_equal(want_pieces[i, k], plane)
+    h.close()
+
+
+# ------------------------------------------------------------------ K3
+def _planes_from_dense(mask_dense):
+    n = mask_dense.shape[0]
+    packed = np.packbits(mask_dense.astype(np.uint8).reshape(n, 24, 8), axis=2, bitorder="little").reshape(n, 24)
+    return np.ascontiguousarray(packed.view(np.uint64).reshape(n, 3).T)
+
+
+def test_masked_head_matches_reference_golden(torch):
+    from bbgpu import capi
+    g = np.load(os.path.join(G, "policy_golden.npz"))
+    n = g["logits"].shape[0]
+    logits = torch.from_numpy(g["logits"]).cuda().contiguous()
+    planes = torch.from_numpy(_planes_from_dense(g["mask"]).view(np.int64)).cuda()
+    act = torch.from_numpy(g["actions"].astype(np.int32)).cuda()
+    logp = torch.empty(n, dtype=torch.float32, device="cuda")
+    ent = torch.empty(n, dtype=torch.float32, device="cuda")
+    capi.masked_sample(logits, planes, n, 0, 0, 2, act, logp, ent)          # evaluate given actions
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(logp.cpu().numpy(), g["log_prob"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent.cpu().numpy(), g["entropy"], rtol=1e-5, atol=1e-6)
+    act2 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    capi.masked_sample(logits, planes, n, 0, 0, 1, act2, logp, ent)         # deterministic
+    torch.cuda.synchronize()
+    assert np.array_equal(act2.cpu().numpy(), g["argmax"])
+    np.testing.assert_allclose(logp.cpu().numpy(), g["log_prob_argmax"], rtol=1e-5, atol=1e-6)
+
+
+def test_masked_head_vs_oracle_random_rows(torch):
+    from bbgpu import capi
+    from oracle import bb_oracle as O
+    rs = np.random.RandomState(4)
+    n = 5000
+    logits = (rs.randn(n, 192) * 4).astype(np.float32)
+    dense = rs.rand(n, 192) < rs.rand(n, 1) * 0.5
+    dense[np.arange(n), rs.randint(0, 192, n)] = True          # at least one valid action
+    dense[0] = False; dense[0, 191] = True                      # single valid action
+    dense[1] = True                                             # everything valid
+    acts = (rs.rand(n, 192) * dense).argmax(1).astype(np.int32)
+    acts[2] = int(np.where(~dense[2])[0][0]) if (~dense[2]).any() else acts[2]   # an INVALID action
+    probs, want_lp, want_ent = O.masked_policy_terms(logits, dense, acts)
+    tl = torch.from_numpy(logits).cuda()
+    planes = torch.from_numpy(_planes_from_dense(dense).view(np.int64)).cuda()
+    ta = torch.from_numpy(acts).cuda()
+    lp = torch.empty(n, dtype=torch.float32, device="cuda")
+    en = torch.empty(n, dtype=torch.float32, device="cuda")
+    capi.masked_sample(tl, planes, n, 0, 0, 2, ta, lp, en)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(lp.cpu().numpy(), want_lp, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(en.cpu().numpy(), want_ent, rtol=2e-5, atol=2e-6)
+    # bf16 logits: same maths on the rounded inputs
+    tb = tl.bfloat16()
+    _, want_lp16, want_ent16 = O.masked_policy_terms(tb.float().cpu().numpy(), dense, acts)
+    capi.masked_sample(tb.contiguous(), planes, n, 0, 0, 2, ta, lp, en)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(lp.cpu().numpy(), want_lp16, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(en.cpu().numpy(), want_ent16, rtol=2e-5, atol=2e-6)
+
+
+def test_sampling_is_valid_reproducible_and_distributed_like_softmax(torch):
+    """Sampling cannot be bit-matched to torch.multinomial: check that every
+    sample is a valid action, the Philox stream is reproducible and matches the host
+    replica's inverse CDF, and frequencies pass a chi-square test."""
+    from bbgpu import capi, philox
+    from oracle import bb_oracle as O
+    rs = np.random.RandomState(6)
+    n = 200000
+    row_logits = (rs.randn(192) * 1.5).astype(np.float32)
+    row_mask = rs.rand(192) < 0.3
+    row_mask[5] = True
+    logits = torch.from_numpy(np.tile(row_logits, (n, 1))).cuda()
+    dense = np.tile(row_mask, (n, 1))
+    planes = torch.from_numpy(_planes_from_dense(dense).view(np.int64)).cuda()
+    a1 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    a2 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    lp = torch.empty(n, dtype=torch.float32, device="cuda")
+    capi.masked_sample(logits, planes, n, 99, 7, 0, a1, lp, None)
+    capi.masked_sample(logits, planes, n, 99, 7, 0, a2, None, None)
+    torch.cuda.synchronize()
+    s = a1.cpu().numpy()
+    assert np.array_equal(s, a2.cpu().numpy())
+    assert row_mask[s].all()
+    probs, _, _ = O.masked_policy_terms(row_logits[None], row_mask[None], np.array([5]))
+    probs = probs[0].astype(np.float64)
+    # host replica of the inverse CDF (same uniforms)
+    u = philox.sample_uniforms(99, 7, n).astype(np.float64)
+    cdf = np.cumsum(probs)
+    host = np.searchsorted(cdf, u * cdf[-1], side="right")
+    assert (host == s).mean() > 0.9999        # float32 vs float64 prefix sums may differ at bin edges
+    cnt = np.bincount(s, minlength=192)[row_mask].astype(np.float64)
+    exp = probs[row_mask] / probs[row_mask].sum() * n
+    keep = exp > 5
+    chi2 = ((cnt[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    dof = keep.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+    # log-prob of the sampled action is log p[a]
+    np.testing.assert_allclose(lp.cpu().numpy(), np.log(probs[s]).astype(np.float32), rtol=1e-4, atol=1e-5)
+    # a different call counter gives a different draw
+    capi.masked_sample(logits, planes, n, 99, 8, 0, a2, None, None)
+    torch.cuda.synchronize()
+    assert (a2.cpu().numpy() != s).mean() > 0.5
