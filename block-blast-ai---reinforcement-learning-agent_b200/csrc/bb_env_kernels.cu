@@ -17,13 +17,13 @@
 #include "bb_kernels.h"
 
 // statically initialised (arrays are padded to 40 entries, the tail is zero)
-__constant__ BBTables c_bb_tables = {BB_PIECE_MASKS, BB_PIECE_INB, BB_PIECE_META};
+__constant__ BBTables c_bb_tables = {BB_PIECE_MASKS, BB_PIECE_INB, BB_PIECE_OFFS, BB_PIECE_META};
 
 __device__ __forceinline__ void bb_stage_tables(BBTables* sh) {
-    // 43 entries of each array; 256 threads: thread k copies entry k of each table
-    for (int k = threadIdx.x; k < BB_NUM_PIECES + 3; k += blockDim.x) {
+    for (int k = threadIdx.x; k < BB_TABLE_N; k += blockDim.x) {
         sh->mask[k] = c_bb_tables.mask[k];
         sh->inb[k] = c_bb_tables.inb[k];
+        sh->offs[k] = c_bb_tables.offs[k];
         sh->meta[k] = c_bb_tables.meta[k];
     }
     __syncthreads();
@@ -44,6 +44,86 @@ __device__ __forceinline__ void bb_store_state(const BBEnvArrays& E, int64_t i, 
     E.s2[i] = make_uint4((uint32_t)s.max_streak, (uint32_t)s.blocks_total, s.draw_ctr, s.policy_ctr);
 }
 
+__device__ __forceinline__ uint64_t bb_shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative trio regeneration (engine.py:155-238).
+//
+// Every lane whose env placed its third piece (`pending`) draws candidate trios from its
+// Philox stream until one is solvable (<= 100 draws).  Most candidates are settled by
+// bb_classify in the owning lane.  The HARD ones (a search is needed) are resolved by the
+// whole warp: the hard lanes are found with a ballot, the 32 lanes are split into equal teams
+// (one per hard item, popc/fns), each team fetches its item from the owner lane with
+// shuffles, every lane evaluates ONE branch of the search (bb_branch), a ballot collects the
+// results, and teams are re-formed for the items still open — so when one heavy item is left
+// all 32 lanes work on it.  The answer is a boolean OR over branches, hence identical to the
+// sequential search whatever the team sizes.
+// All 32 lanes of the warp must call this (lanes without work pass pending = false).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, const BBTables* T,
+                                                 uint64_t seed, uint64_t env_id, uint32_t& pieces,
+                                                 uint32_t& draw_ctr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t attempts = 0;
+    while (__any_sync(FULL, pending)) {
+        BBItem item;
+        item.b = board; item.v[0] = item.v[1] = item.v[2] = 0; item.plan = 0;
+        uint32_t trio = 0;
+        bool hard = false;
+        if (pending) {
+            trio = bb_draw_trio(seed, env_id, draw_ctr);
+            draw_ctr += 1;
+            attempts += 1;
+            pieces = trio;                      // used bits cleared (engine.py:165)
+            BBPiece P[3] = {bb_piece(T, trio & 0xFFu), bb_piece(T, (trio >> 8) & 0xFFu), bb_piece(T, (trio >> 16) & 0xFFu)};
+            const int cls = bb_classify(board, P, &item);
+            if (cls == BB_ACCEPT) pending = false;
+            else if (cls == BB_REJECT) pending = attempts < 100u;     // 100th failure: keep it (engine.py:171-172)
+            else hard = true;
+        }
+        uint32_t next = 0;                      // owner: first branch not yet handed out
+        unsigned hmask = __ballot_sync(FULL, hard);
+        while (hmask) {
+            const int H = __popc(hmask);
+            const int ts = 32 / H;              // team size (>= 1)
+            const int g = lane / ts;            // my team; teams >= H have no item
+            const bool in_team = g < H;
+            const int owner = in_team ? (int)__fns(hmask, 0, g + 1) : lane;
+            BBItem it;
+            it.b = bb_shfl64(item.b, owner);
+            it.v[0] = bb_shfl64(item.v[0], owner);
+            it.v[1] = bb_shfl64(item.v[1], owner);
+            it.v[2] = bb_shfl64(item.v[2], owner);
+            it.plan = __shfl_sync(FULL, item.plan, owner);
+            const uint32_t tr = __shfl_sync(FULL, trio, owner);
+            const uint32_t t = __shfl_sync(FULL, next, owner) + (uint32_t)(lane - g * ts);
+            bool f = false;
+            if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) {
+                BBPiece P[3] = {bb_piece(T, tr & 0xFFu), bb_piece(T, (tr >> 8) & 0xFFu), bb_piece(T, (tr >> 16) & 0xFFu)};
+                f = bb_branch(it, P, t);
+            }
+            const unsigned fm = __ballot_sync(FULL, f);
+            if (hard) {
+                const int my = __popc(hmask & ((1u << lane) - 1u));          // index of the team working for me
+                const unsigned tm = (ts == 32 ? FULL : ((1u << ts) - 1u)) << (my * ts);
+                next += (uint32_t)ts;
+                if (fm & tm) { hard = false; pending = false; }               // solvable: accept
+                else if (next >= BB_PLAN_NA(item.plan) + BB_PLAN_NB(item.plan)) {
+                    hard = false;                                             // exhausted: reject
+                    pending = attempts < 100u;
+                }
+            }
+            hmask = __ballot_sync(FULL, hard);
+        }
+    }
+    return attempts;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: one env step per thread; RANDOM fuses the uniform-random-valid policy and may run
 // n_steps back to back with the state held in registers.
@@ -60,26 +140,41 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < E.n;
     unsigned long long st_eps = 0, st_score = 0, st_len = 0;
+    BBState s;
+    BBStepOut o;
+    int action = 0;
+    const uint64_t env_id = (uint64_t)(E.env_offset + (live ? i : 0));
     if (live) {
-        BBState s;
         bb_load_state(E, i, s);
-        const uint64_t env_id = (uint64_t)(E.env_offset + i);
-        BBStepOut o;
-        int action = 0;
-        if (RANDOM) {
-            bb_action_mask(s, &T, o.mask);
-            for (int step = 0; step < n_steps; ++step) {
+        if (RANDOM) bb_action_mask(s, &T, o.mask);
+        else action = actions[i];
+    } else {
+        s.board = 0; s.pieces = 0; s.aux = 0; s.draw_ctr = 0; s.policy_ctr = 0;
+        s.score = s.streak = s.moves = s.lines_total = s.max_streak = s.blocks_total = 0;
+        o.mask[0] = o.mask[1] = o.mask[2] = 0;
+    }
+    const int steps = RANDOM ? n_steps : 1;
+    for (int step = 0; step < steps; ++step) {
+        BBMove mv;
+        mv.ok = false; mv.needs_deal = false; mv.n = 0; mv.lines = 0; mv.gain = 0;
+        if (live) {
+            if (RANDOM) {
                 const BBPhilox4 r = bb_philox((uint32_t)env_id, (uint32_t)(env_id >> 32), s.policy_ctr,
                                               BB_STREAM_POLICY, (uint32_t)E.seed, (uint32_t)(E.seed >> 32));
                 s.policy_ctr += 1;
                 action = bb_pick_action(o.mask, r.x);
-                bb_env_apply(s, action, &T, cfg, E.seed, env_id, E.flags, o);
-                if (o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
             }
-        } else {
-            action = actions[i];
-            bb_env_apply(s, action, &T, cfg, E.seed, env_id, E.flags, o);
+            mv = bb_env_pre(s, action, &T, o);
         }
+        // all 32 lanes take part in the deal, with or without work of their own
+        const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, E.seed, env_id,
+                                            s.pieces, s.draw_ctr);
+        if (live && mv.ok) {
+            bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o);
+            if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
+        }
+    }
+    if (live) {
         bb_store_state(E, i, s);
         if (RANDOM && actions_out) actions_out[i] = action;
         if (rewards) rewards[i] = o.reward;
@@ -127,7 +222,7 @@ bb_reset_kernel(BBEnvArrays E, const uint8_t* __restrict__ reset_mask, uint64_t*
     BBState s;
     bb_load_state(E, i, s);
     if (!reset_mask || reset_mask[i]) {
-        bb_reset_state(s, &T, E.seed, (uint64_t)(E.env_offset + i), E.flags);
+        bb_reset_state(s, E.seed, (uint64_t)(E.env_offset + i), E.flags);
         bb_store_state(E, i, s);
     }
     if (mask_out) {

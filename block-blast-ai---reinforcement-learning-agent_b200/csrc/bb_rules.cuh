@@ -3,27 +3,27 @@
 //
 // Bit convention: bit = row*8 + col (same as the action codec a % 64,
 // reference src/environment/block_blast_env.py:114-118).  A piece is its cell mask with the
-// top-left of its bounding box at bit 0 plus the mask of anchors that keep it on the board.
+// top-left of its bounding box at bit 0, the mask of anchors that keep it on the board, and
+// the list of its cell offsets.
 //
 // What each function restates (file:line in the reference):
-//   bb_valid      Board.can_place for all 64 anchors at once      src/game/board.py:71-93, :117-142
-//   bb_clear      find_complete_lines + clear_lines               src/game/board.py:144-193
-//   bb_holes      Board.count_holes                               src/game/board.py:195-216
-//   bb_center     filled cells of rows/cols 2..5                  src/game/board.py:236-243
-//   bb_solvable   _can_place_all_pieces (boolean; order is free)  src/game/engine.py:174-238
-//   bb_score_gain _calculate_score with post-increment streak     src/game/engine.py:240-312, :419-429
-//   bb_reward     _calculate_reward, float64, same op order       src/environment/block_blast_env.py:148-193
-//   bb_env_apply  BlockBlastEnv.step + make_move + auto-reset     block_blast_env.py:224-264, engine.py:390-454,
-//                                                                 src/environment/wrappers.py:93-108
+//   bb_valid        Board.can_place for all 64 anchors at once     src/game/board.py:71-93, :117-142
+//   bb_clear        find_complete_lines + clear_lines              src/game/board.py:144-193
+//   bb_holes        Board.count_holes                              src/game/board.py:195-216
+//   bb_center       filled cells of rows/cols 2..5                 src/game/board.py:236-243
+//   bb_classify /   _can_place_all_pieces (a boolean, so the       src/game/engine.py:174-238
+//   bb_branch       search order is free)
+//   bb_env_pre      BlockBlastEnv.step validation + make_move up   block_blast_env.py:224-245,
+//                   to the trio regeneration                       engine.py:390-437
+//   bb_env_post     game over, reward, auto-reset, next mask       engine.py:440-441, block_blast_env.py:148-193,
+//                                                                  src/environment/wrappers.py:96-102
 #pragma once
 #include <stdint.h>
 
 #if defined(__CUDACC__)
 #define BB_HD __host__ __device__ __forceinline__
-#define BB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define BB_HD inline
-#define BB_HD_NOINLINE static
 #endif
 
 #include "bb_piece_table.inc"
@@ -31,10 +31,12 @@
 // ---------------------------------------------------------------------------------------
 // tables
 // ---------------------------------------------------------------------------------------
+#define BB_TABLE_N (BB_NUM_PIECES + 3)
 struct BBTables {
-    uint64_t mask[BB_NUM_PIECES + 3];   // piece cells at the origin (padded: slots 37..39 = 0)
-    uint64_t inb[BB_NUM_PIECES + 3];    // anchors whose bounding box stays on the board
-    uint32_t meta[BB_NUM_PIECES + 3];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
+    uint64_t mask[BB_TABLE_N];   // piece cells at the origin (slots 37..39 are zero padding)
+    uint64_t inb[BB_TABLE_N];    // anchors whose bounding box stays on the board
+    uint64_t offs[BB_TABLE_N];   // cell offsets, 6 bits each: bits 0..29 = #0..4, bits 32..55 = #5..8
+    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
 };
 
 #define BB_META_N(m) ((m) & 0xFu)
@@ -43,14 +45,24 @@ struct BBTables {
 
 static const uint64_t BB_HOST_PIECE_MASKS[BB_NUM_PIECES] = BB_PIECE_MASKS;
 static const uint64_t BB_HOST_PIECE_INB[BB_NUM_PIECES] = BB_PIECE_INB;
+static const uint64_t BB_HOST_PIECE_OFFS[BB_NUM_PIECES] = BB_PIECE_OFFS;
 static const uint32_t BB_HOST_PIECE_META[BB_NUM_PIECES] = BB_PIECE_META;
 
 inline void bb_fill_tables(BBTables* t) {
-    for (int i = 0; i < BB_NUM_PIECES + 3; ++i) {
+    for (int i = 0; i < BB_TABLE_N; ++i) {
         t->mask[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_MASKS[i] : 0;
         t->inb[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_INB[i] : 0;
+        t->offs[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_OFFS[i] : 0;
         t->meta[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_META[i] : 0;
     }
+}
+
+struct BBPiece { uint64_t pm, inb, offs; uint32_t meta; };
+
+BB_HD BBPiece bb_piece(const BBTables* T, uint32_t id) {
+    BBPiece p;
+    p.pm = T->mask[id]; p.inb = T->inb[id]; p.offs = T->offs[id]; p.meta = T->meta[id];
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -65,7 +77,8 @@ BB_HD int bb_popc(uint64_t x) {
 }
 BB_HD int bb_ctz(uint64_t x) {   // x != 0
 #if defined(__CUDA_ARCH__)
-    return __ffsll((long long)x) - 1;
+    const uint32_t lo = (uint32_t)x;
+    return lo ? (__ffs((int)lo) - 1) : (31 + __ffs((int)(uint32_t)(x >> 32)));
 #else
     return __builtin_ctzll(x);
 #endif
@@ -77,6 +90,17 @@ BB_HD uint32_t bb_mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+// position of the k-th (0-based) set bit of w; k < popcount(w)
+BB_HD int bb_select(uint64_t w, int k) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+    const int c = __popc(lo);
+    return k < c ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - c + 1);
+#else
+    for (int i = 0; i < k; ++i) w &= w - 1;
+    return __builtin_ctzll(w);
+#endif
+}
 
 #define BB_COL_A 0x0101010101010101ull
 #define BB_COL_H 0x8080808080808080ull
@@ -85,14 +109,35 @@ BB_HD uint32_t bb_mulhi(uint32_t a, uint32_t b) {
 // ---------------------------------------------------------------------------------------
 // board primitives
 // ---------------------------------------------------------------------------------------
-// All anchors at which the piece (cells pm, in-bounds anchors inb) fits on the EMPTY-cell
-// set e = ~board.  board.py:71-93 evaluated for 64 anchors with one shift-AND per block.
-BB_HD uint64_t bb_valid(uint64_t e, uint64_t pm, uint64_t inb) {
-    uint64_t v = inb;
-    while (pm) {                    // one shift-AND per block of the piece (<= 9)
-        const int o = bb_ctz(pm);
-        v &= e >> o;
-        pm &= pm - 1;
+// e >> o for 0 <= o <= 32
+BB_HD uint64_t bb_shr(uint64_t e, uint32_t o) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = (uint32_t)e, hi = (uint32_t)(e >> 32);
+    return (uint64_t)__funnelshift_rc(lo, hi, o) | ((uint64_t)__funnelshift_rc(hi, 0u, o) << 32);
+#else
+    return e >> o;
+#endif
+}
+
+// All anchors at which piece p fits on the EMPTY-cell set e = ~board: board.py:71-93 for the
+// 64 anchors at once, one shift-AND per cell of the piece.  The offset list is padded with
+// repeats, so the first four steps need no predicate (31 of 37 pieces have <= 4 cells).
+BB_HD uint64_t bb_valid(uint64_t e, const BBPiece& p) {
+    const uint32_t lo = (uint32_t)p.offs, hi = (uint32_t)(p.offs >> 32);
+    uint64_t v = p.inb;
+    v &= bb_shr(e, lo & 63u);
+    v &= bb_shr(e, (lo >> 6) & 63u);
+    v &= bb_shr(e, (lo >> 12) & 63u);
+    v &= bb_shr(e, (lo >> 18) & 63u);
+    const uint32_t n = BB_META_N(p.meta);
+    if (n > 4) {
+        v &= bb_shr(e, (lo >> 24) & 63u);
+        v &= bb_shr(e, hi & 63u);
+        if (n > 6) {
+            v &= bb_shr(e, (hi >> 6) & 63u);
+            v &= bb_shr(e, (hi >> 12) & 63u);
+            v &= bb_shr(e, (hi >> 18) & 63u);
+        }
     }
     return v;
 }
@@ -139,6 +184,36 @@ BB_HD int bb_holes(uint64_t b) {
 
 BB_HD int bb_center(uint64_t b) { return bb_popc(b & BB_CENTER); }
 
+// Line occupancy summary of a board: byte r of `rows` = filled cells of row r; nibble c of
+// `cols` = min(filled cells of column c, 15).  Used for "can a piece complete a line" bounds.
+struct BBLines { uint64_t rows; uint32_t cols; };
+
+BB_HD BBLines bb_lines(uint64_t b) {
+    BBLines L;
+    uint64_t t = b - ((b >> 1) & 0x5555555555555555ull);
+    t = (t & 0x3333333333333333ull) + ((t >> 2) & 0x3333333333333333ull);
+    L.rows = (t + (t >> 4)) & 0x0F0F0F0F0F0F0F0Full;
+    uint32_t cols = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // columns k and k+4 live in the low / high nibble of every byte
+        const uint64_t x = (b >> k) & 0x1111111111111111ull;
+        uint32_t s = (uint32_t)x + (uint32_t)(x >> 32);
+        s += s >> 16;
+        s += s >> 8;                // low byte: nibble0 = column k, nibble1 = column k+4
+        cols |= ((s & 0xFu) << (4 * k)) | (((s >> 4) & 0xFu) << (4 * (k + 4)));
+    }
+    L.cols = cols;
+    return L;
+}
+// exists a row with at most m empty cells / a column with at most m empty cells (1 <= m <= 7)
+BB_HD bool bb_row_within(const BBLines& L, int m) {
+    return ((L.rows + (uint64_t)(0x78 + m) * BB_COL_A) & BB_COL_H) != 0;   // count + 120 + m >= 128
+}
+BB_HD bool bb_col_within(const BBLines& L, int m) {
+    return ((L.cols + (uint32_t)m * 0x11111111u) & 0x88888888u) != 0;       // count + m >= 8
+}
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Stream layout documented in philox.py.
 // ---------------------------------------------------------------------------------------
@@ -174,191 +249,174 @@ BB_HD uint32_t bb_draw_trio(uint64_t seed, uint64_t env_id, uint32_t draw) {
 // ---------------------------------------------------------------------------------------
 // trio solvability (engine.py:174-238).  The reference enumerates piece orders and anchors
 // depth-first with line clears after every simulated placement and returns a boolean, so any
-// sound and complete search gives the identical result.  Facts used to prune:
+// sound and complete search gives the identical result.  Facts used:
 //   (M) clearing lines only removes cells, so a placement that fits before a clear fits after.
 //   (P) hence if the three pieces have pairwise-disjoint placements that all fit on the
 //       current board, every order works ("packing"), no simulation needed;
 //   (C) conversely a solution that is NOT a packing must complete a line with its first or
 //       second placement; a line with `miss` empty cells can only be completed by pieces that
 //       can put at least `miss` cells into one row (column): meta maxrow / maxcol.
+// The search is cut into independent BRANCHES (one first-level placement each) so that the
+// kernel can spread one hard (board, trio) item over a team of lanes:
+//   stage A branch t < nA : x at its t-th anchor, then a packing of y and z beside it
+//   stage B branch        : piece i at one of its anchors (any order i), then the other two
+//                           with clears simulated; when nothing cleared, only a CLEARING
+//                           second placement is explored (a plain packing is stage A's job)
 // ---------------------------------------------------------------------------------------
 #ifdef BB_COUNT_WORK
-struct BBWork { long long valid_calls, fast_accept, fast_reject, pack_iters, clear_iters, slow; };
+struct BBWork { long long valid_calls, fast_accept, fast_reject, pack_iters, clear_iters, slow, branches; };
 static BBWork g_bb_work;
 #define BB_WORK(f, n) (g_bb_work.f += (n))
 #else
 #define BB_WORK(f, n) ((void)0)
 #endif
 
-// smallest number of empty cells in any row (*row_miss) and in any column (*col_miss) of b
-BB_HD void bb_min_missing(uint64_t b, int* row_miss, int* col_miss) {
-    int rmax = 0, cmax = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = bb_popc(b & (0xFFull << (8 * i)));
-        const int c = bb_popc(b & (BB_COL_A << i));
-        rmax = r > rmax ? r : rmax;
-        cmax = c > cmax ? c : cmax;
-    }
-    *row_miss = 8 - rmax;
-    *col_miss = 8 - cmax;
-}
+enum { BB_REJECT = 0, BB_ACCEPT = 1, BB_HARD = 2 };
 
-struct BBTrio { uint64_t pm[3], inb[3]; uint32_t meta[3]; };
+struct BBItem {
+    uint64_t b;        // board the trio must be placeable on
+    uint64_t v[3];     // valid anchors of each piece on b
+    uint32_t plan;     // bits 0-1 x, 2-3 y, 4-5 z (stage-A order); bits 8-15 nA; bits 16-23 nB
+};
+#define BB_PLAN_NA(p) (((p) >> 8) & 0xFFu)
+#define BB_PLAN_NB(p) (((p) >> 16) & 0xFFu)
 
-BB_HD void bb_load_trio(const BBTables* T, uint32_t trio, BBTrio* t) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint32_t id = (trio >> (8 * i)) & 0xFFu;
-        t->pm[i] = T->mask[id];
-        t->inb[i] = T->inb[id];
-        t->meta[i] = T->meta[id];
-    }
-}
-
-// exists an anchor for piece y on b1 such that, afterwards (with clears), piece z still fits?
-// "pack2": z fits beside y without needing a clear.
-BB_HD bool bb_pack2(uint64_t b, uint64_t pmy, uint64_t inby, uint64_t pmz, uint64_t inbz) {
-    uint64_t vy = bb_valid(~b, pmy, inby);
+// z fits beside some placement of y on b (no clear needed)
+BB_HD bool bb_pack2(uint64_t b, const BBPiece& y, const BBPiece& z) {
+    uint64_t vy = bb_valid(~b, y);
     BB_WORK(valid_calls, 1);
     while (vy) {
         const int a = bb_ctz(vy);
         vy &= vy - 1;
         BB_WORK(pack_iters, 1);
         BB_WORK(valid_calls, 1);
-        if (bb_valid(~(b | (pmy << a)), pmz, inbz)) return true;
+        if (bb_valid(~(b | (y.pm << a)), z)) return true;
     }
     return false;
 }
 
-// exists a CLEARING placement of x on b after which y fits (one order only)
-BB_HD bool bb_clear_then_fit(uint64_t b, uint64_t pmx, uint64_t inbx, uint64_t pmy, uint64_t inby) {
-    uint64_t vx = bb_valid(~b, pmx, inbx);
+// exists a CLEARING placement of x on b after which y fits
+BB_HD bool bb_clear_then_fit(uint64_t b, const BBPiece& x, const BBPiece& y) {
+    uint64_t vx = bb_valid(~b, x);
     BB_WORK(valid_calls, 1);
     while (vx) {
         const int a = bb_ctz(vx);
         vx &= vx - 1;
-        const uint64_t b1 = b | (pmx << a);
+        const uint64_t b1 = b | (x.pm << a);
         BB_WORK(clear_iters, 1);
         if (bb_any_full(b1)) {
             BB_WORK(valid_calls, 1);
-            if (bb_valid(~bb_clear_only(b1), pmy, inby)) return true;
+            if (bb_valid(~bb_clear_only(b1), y)) return true;
         }
     }
     return false;
 }
 
-// two pieces on board b, any order, clears simulated: engine.py:181-224 at depth 1
-BB_HD bool bb_solve2(uint64_t b, const BBTrio* t, int j, int k, bool skip_pack) {
-    int rm, cm;
-    if (!skip_pack && bb_pack2(b, t->pm[j], t->inb[j], t->pm[k], t->inb[k])) return true;
-    bb_min_missing(b, &rm, &cm);
-    const int mrj = (int)BB_META_MAXROW(t->meta[j]), mcj = (int)BB_META_MAXCOL(t->meta[j]);
-    const int mrk = (int)BB_META_MAXROW(t->meta[k]), mck = (int)BB_META_MAXCOL(t->meta[k]);
-    if ((rm <= mrj || cm <= mcj) && bb_clear_then_fit(b, t->pm[j], t->inb[j], t->pm[k], t->inb[k])) return true;
-    if ((rm <= mrk || cm <= mck) && bb_clear_then_fit(b, t->pm[k], t->inb[k], t->pm[j], t->inb[j])) return true;
+// two pieces on board b, any order, clears simulated (engine.py:181-224 at depth 1)
+BB_HD bool bb_solve2(uint64_t b, const BBPiece& j, const BBPiece& k, bool skip_pack) {
+    if (!skip_pack && bb_pack2(b, j, k)) return true;
+    const BBLines L = bb_lines(b);
+    if ((bb_row_within(L, (int)BB_META_MAXROW(j.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(j.meta))) &&
+        bb_clear_then_fit(b, j, k)) return true;
+    if ((bb_row_within(L, (int)BB_META_MAXROW(k.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(k.meta))) &&
+        bb_clear_then_fit(b, k, j)) return true;
     return false;
 }
 
-enum { BB_REJECT = 0, BB_ACCEPT = 1, BB_HARD = 2 };
+// fact (C) for three pieces: can the two largest per-line contributions complete any line?
+BB_HD bool bb_clear_reachable(uint64_t b, const BBPiece P[3]) {
+    const int r0 = (int)BB_META_MAXROW(P[0].meta), r1 = (int)BB_META_MAXROW(P[1].meta), r2 = (int)BB_META_MAXROW(P[2].meta);
+    const int c0 = (int)BB_META_MAXCOL(P[0].meta), c1 = (int)BB_META_MAXCOL(P[1].meta), c2 = (int)BB_META_MAXCOL(P[2].meta);
+    const int rmin = r0 < r1 ? (r0 < r2 ? r0 : r2) : (r1 < r2 ? r1 : r2);
+    const int cmin = c0 < c1 ? (c0 < c2 ? c0 : c2) : (c1 < c2 ? c1 : c2);
+    const int rt = r0 + r1 + r2 - rmin, ct = c0 + c1 + c2 - cmin;
+    if (rt >= 8 || ct >= 8) return true;      // two pieces could even fill an empty line
+    const BBLines L = bb_lines(b);
+    return bb_row_within(L, rt) || bb_col_within(L, ct);
+}
 
-// Cheap classification of (board, trio): ACCEPT / REJECT when provable in O(1) valid-mask
-// evaluations, HARD otherwise.  v[] receives the three valid-anchor masks on b.
-BB_HD int bb_solvable_fast(uint64_t b, const BBTrio* t, uint64_t v[3]) {
+// Cheap classification of (board, trio): ACCEPT / REJECT when provable with a handful of
+// valid-mask evaluations, else HARD with the item's branch plan filled in.
+BB_HD int bb_classify(uint64_t b, const BBPiece P[3], BBItem* it) {
     const uint64_t e = ~b;
-    v[0] = bb_valid(e, t->pm[0], t->inb[0]);
-    v[1] = bb_valid(e, t->pm[1], t->inb[1]);
-    v[2] = bb_valid(e, t->pm[2], t->inb[2]);
+    it->b = b;
+    it->v[0] = bb_valid(e, P[0]);
+    it->v[1] = bb_valid(e, P[1]);
+    it->v[2] = bb_valid(e, P[2]);
     BB_WORK(valid_calls, 3);
-    if (v[0] && v[1] && v[2]) {
-        // greedy packing: the piece with the fewest anchors first, lowest anchors
-        const int n0 = bb_popc(v[0]), n1 = bb_popc(v[1]), n2 = bb_popc(v[2]);
+    const int n0 = bb_popc(it->v[0]), n1 = bb_popc(it->v[1]), n2 = bb_popc(it->v[2]);
+    uint32_t nA = 0, order = 0;
+    if (n0 && n1 && n2) {
+        // greedy packing: fewest anchors first, lowest anchors
         int x = 0, y = 1, z = 2;
         if (n1 < n0 && n1 <= n2) { x = 1; y = 0; }
         else if (n2 < n0 && n2 < n1) { x = 2; z = 0; }
-        // y before z: fewer anchors first
         const int ny = (y == 0 ? n0 : (y == 1 ? n1 : n2)), nz = (z == 0 ? n0 : (z == 1 ? n1 : n2));
         if (nz < ny) { const int s = y; y = z; z = s; }
-        const uint64_t b1 = b | (t->pm[x] << bb_ctz(v[x]));
-        const uint64_t vy = bb_valid(~b1, t->pm[y], t->inb[y]);
+        const uint64_t b1 = b | (P[x].pm << bb_ctz(it->v[x]));
+        const uint64_t vy = bb_valid(~b1, P[y]);
         BB_WORK(valid_calls, 1);
         if (vy) {
-            const uint64_t b2 = b1 | (t->pm[y] << bb_ctz(vy));
+            // lowest and highest anchor of y: two cheap tries
             BB_WORK(valid_calls, 1);
-            if (bb_valid(~b2, t->pm[z], t->inb[z])) return BB_ACCEPT;
+            if (bb_valid(~(b1 | (P[y].pm << bb_ctz(vy))), P[z])) return BB_ACCEPT;
+            const int ah = 63 - (int)
+#if defined(__CUDA_ARCH__)
+                __clzll((long long)vy);
+#else
+                __builtin_clzll(vy);
+#endif
+            BB_WORK(valid_calls, 1);
+            if (bb_valid(~(b1 | (P[y].pm << ah)), P[z])) return BB_ACCEPT;
         }
-        return BB_HARD;
+        nA = (uint32_t)(x == 0 ? n0 : (x == 1 ? n1 : n2));
+        order = (uint32_t)x | ((uint32_t)y << 2) | ((uint32_t)z << 4);
     }
-    // some piece has no anchor now: only a line clear can make room (fact M/C)
-    int rm, cm;
-    bb_min_missing(b, &rm, &cm);
-    // the two largest per-line contributions among the three pieces
-    int r0 = (int)BB_META_MAXROW(t->meta[0]), r1 = (int)BB_META_MAXROW(t->meta[1]), r2 = (int)BB_META_MAXROW(t->meta[2]);
-    int c0 = (int)BB_META_MAXCOL(t->meta[0]), c1 = (int)BB_META_MAXCOL(t->meta[1]), c2 = (int)BB_META_MAXCOL(t->meta[2]);
-    const int rmin = r0 < r1 ? (r0 < r2 ? r0 : r2) : (r1 < r2 ? r1 : r2);
-    const int cmin = c0 < c1 ? (c0 < c2 ? c0 : c2) : (c1 < c2 ? c1 : c2);
-    const int rtop2 = r0 + r1 + r2 - rmin, ctop2 = c0 + c1 + c2 - cmin;
-    if (rm > rtop2 && cm > ctop2) return BB_REJECT;
+    // stage B is only worth exploring if some line can be completed at all (fact C)
+    const uint32_t nB = bb_clear_reachable(b, P) ? (uint32_t)(n0 + n1 + n2) : 0u;
+    it->plan = order | (nA << 8) | (nB << 16);
+    if (nA + nB == 0) return BB_REJECT;
     return BB_HARD;
 }
 
-// Exact search for the cases bb_solvable_fast leaves open.  v[] = valid masks on b.
-BB_HD_NOINLINE bool bb_solvable_slow(uint64_t b, const BBTrio* t, const uint64_t v[3]) {
-    BB_WORK(slow, 1);
-    // Stage A (fact P): a packing of all three.
-    if (v[0] && v[1] && v[2]) {
-        const int n0 = bb_popc(v[0]), n1 = bb_popc(v[1]), n2 = bb_popc(v[2]);
-        int x = 0, y = 1, z = 2;
-        if (n1 < n0 && n1 <= n2) { x = 1; y = 0; }
-        else if (n2 < n0 && n2 < n1) { x = 2; z = 0; }
-        uint64_t vx = v[x];
-        while (vx) {
-            const int a = bb_ctz(vx);
-            vx &= vx - 1;
-            const uint64_t b1 = b | (t->pm[x] << a);
-            // z must still fit on b1 at all, else no packing through this anchor
-            BB_WORK(valid_calls, 1);
-            if (!bb_valid(~b1, t->pm[z], t->inb[z])) continue;
-            if (bb_pack2(b1, t->pm[y], t->inb[y], t->pm[z], t->inb[z])) return true;
-        }
+// one branch of a HARD item; t in [0, nA + nB)
+BB_HD bool bb_branch(const BBItem& it, const BBPiece P[3], uint32_t t) {
+    BB_WORK(branches, 1);
+    const uint32_t nA = BB_PLAN_NA(it.plan);
+    if (t < nA) {
+        const int x = (int)(it.plan & 3u), y = (int)((it.plan >> 2) & 3u), z = (int)((it.plan >> 4) & 3u);
+        const uint64_t b1 = it.b | (P[x].pm << bb_select(it.v[x], (int)t));
+        BB_WORK(valid_calls, 1);
+        if (!bb_valid(~b1, P[z])) return false;       // z must still fit at all
+        return bb_pack2(b1, P[y], P[z]);
     }
-    // Stage B (fact C): a solution must clear a line with its 1st or 2nd placement.
-    int rm, cm;
-    bb_min_missing(b, &rm, &cm);
-    {
-        int r0 = (int)BB_META_MAXROW(t->meta[0]), r1 = (int)BB_META_MAXROW(t->meta[1]), r2 = (int)BB_META_MAXROW(t->meta[2]);
-        int c0 = (int)BB_META_MAXCOL(t->meta[0]), c1 = (int)BB_META_MAXCOL(t->meta[1]), c2 = (int)BB_META_MAXCOL(t->meta[2]);
-        const int rmin = r0 < r1 ? (r0 < r2 ? r0 : r2) : (r1 < r2 ? r1 : r2);
-        const int cmin = c0 < c1 ? (c0 < c2 ? c0 : c2) : (c1 < c2 ? c1 : c2);
-        if (rm > r0 + r1 + r2 - rmin && cm > c0 + c1 + c2 - cmin) return false;
-    }
-    for (int i = 0; i < 3; ++i) {
-        const int j = i == 0 ? 1 : 0, k = i == 2 ? 1 : 2;
-        uint64_t vi = v[i];
-        while (vi) {
-            const int a = bb_ctz(vi);
-            vi &= vi - 1;
-            const uint64_t b1 = b | (t->pm[i] << a);
-            if (bb_any_full(b1)) {
-                if (bb_solve2(bb_clear_only(b1), t, j, k, false)) return true;
-            } else {
-                // no clear yet: a packing of the other two on b1 would have been found in
-                // stage A, so only a clearing second placement can help
-                if (bb_solve2(b1, t, j, k, true)) return true;
-            }
-        }
-    }
-    return false;
+    int k = (int)(t - nA);
+    int i = 0;
+    const int n0 = bb_popc(it.v[0]), n1 = bb_popc(it.v[1]);
+    if (k >= n0) { k -= n0; i = 1; if (k >= n1) { k -= n1; i = 2; } }
+    const int j = i == 0 ? 1 : 0, l = i == 2 ? 1 : 2;
+    const uint64_t b1 = it.b | (P[i].pm << bb_select(it.v[i], k));
+    if (bb_any_full(b1)) return bb_solve2(bb_clear_only(b1), P[j], P[l], false);
+    // nothing cleared: a packing of the other two on b1 is stage A's business (or impossible),
+    // so only a clearing second placement can help
+    return bb_solve2(b1, P[j], P[l], true);
 }
 
+// sequential driver (host build, reset path): same branches, in index order
 BB_HD bool bb_solvable(uint64_t b, const BBTables* T, uint32_t trio) {
-    BBTrio t;
-    bb_load_trio(T, trio, &t);
-    uint64_t v[3];
-    const int f = bb_solvable_fast(b, &t, v);
+    BBPiece P[3];
+    P[0] = bb_piece(T, trio & 0xFFu);
+    P[1] = bb_piece(T, (trio >> 8) & 0xFFu);
+    P[2] = bb_piece(T, (trio >> 16) & 0xFFu);
+    BBItem it;
+    const int f = bb_classify(b, P, &it);
     if (f == BB_ACCEPT) { BB_WORK(fast_accept, 1); return true; }
     if (f == BB_REJECT) { BB_WORK(fast_reject, 1); return false; }
-    return bb_solvable_slow(b, &t, v);
+    BB_WORK(slow, 1);
+    const uint32_t n = BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan);
+    for (uint32_t t = 0; t < n; ++t)
+        if (bb_branch(it, P, t)) return true;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -421,7 +479,8 @@ BB_HD float bb_reward(const BBRewardCfg& c, int n_blocks, int lines, bool game_o
     return (float)r;
 }
 
-// draw until a solvable trio appears, at most 100 candidates (engine.py:155-172)
+// draw until a solvable trio appears, at most 100 candidates (engine.py:155-172) — the
+// sequential form; the step kernel runs the same loop warp-cooperatively (bb_warp_deal)
 BB_HD uint32_t bb_deal(uint64_t board, const BBTables* T, uint64_t seed, uint64_t env_id, uint32_t* draw_ctr) {
     uint32_t trio = 0;
     for (int attempt = 0; attempt < 100; ++attempt) {
@@ -432,7 +491,7 @@ BB_HD uint32_t bb_deal(uint64_t board, const BBTables* T, uint64_t seed, uint64_
     return trio;   // byte 3 = 0: nothing used
 }
 
-BB_HD void bb_reset_state(BBState& s, const BBTables* T, uint64_t seed, uint64_t env_id, uint32_t flags) {
+BB_HD void bb_reset_state(BBState& s, uint64_t seed, uint64_t env_id, uint32_t flags) {
     if (flags & BB_FLAG_RESEED_ON_RESET) s.draw_ctr = 0;
     s.board = 0;
     s.score = s.streak = s.moves = s.lines_total = s.max_streak = s.blocks_total = 0;
@@ -450,8 +509,7 @@ BB_HD void bb_action_mask(const BBState& s, const BBTables* T, uint64_t m[3]) {
     const bool over = BB_OVER(s);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const uint32_t id = (s.pieces >> (8 * i)) & 0xFFu;
-        const uint64_t v = bb_valid(e, T->mask[id], T->inb[id]);
+        const uint64_t v = bb_valid(e, bb_piece(T, (s.pieces >> (8 * i)) & 0xFFu));
         m[i] = (((used >> i) & 1u) || over) ? 0ull : v;
     }
 }
@@ -465,11 +523,14 @@ struct BBStepOut {
     uint64_t mask[3];      // action mask of the state after the step (after auto-reset)
 };
 
-// One env step with the vec-env's auto-reset.  Invalid action: state untouched, reward -10
-// (block_blast_env.py:240-245).  The post-step action mask is always produced because the
-// game-over test (engine.py:440-441) needs the same three valid masks.
-BB_HD void bb_env_apply(BBState& s, int action, const BBTables* T, const BBRewardCfg& cfg,
-                        uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o) {
+struct BBMove { int n, lines, gain; bool ok, needs_deal; };
+
+// First half of a step: decode + validate (block_blast_env.py:104-118, :240-245,
+// engine.py:326-346), place, clear, streak and score (engine.py:405-429).  On an invalid
+// action the state is untouched and `o` is final (reward -10, mask of the unchanged state).
+BB_HD BBMove bb_env_pre(BBState& s, int action, const BBTables* T, BBStepOut& o) {
+    BBMove mv;
+    mv.n = 0; mv.lines = 0; mv.gain = 0; mv.needs_deal = false;
     const uint32_t used = BB_USED(s);
     const int p = action >> 6;                 // action // 64 (negative actions -> p < 0)
     const int a = action & 63;
@@ -477,18 +538,19 @@ BB_HD void bb_env_apply(BBState& s, int action, const BBTables* T, const BBRewar
     const uint32_t id = ok ? ((s.pieces >> (8 * p)) & 0xFFu) : 0u;
     const uint64_t pm = T->mask[id];
     if (ok) ok = ((T->inb[id] >> a) & 1ull) && (((pm << a) & s.board) == 0ull);
+    mv.ok = ok;
     o.ep_score = 0; o.ep_len = 0; o.gain = 0;
     if (!ok) {
         o.reward = -10.0f;
         o.terminated = 0;
         o.info = 1u;
         bb_action_mask(s, T, o.mask);
-        return;
+        return mv;
     }
     const int n = (int)BB_META_N(T->meta[id]);
     int lines;
     s.board = bb_clear(s.board | (pm << a), &lines);
-    uint32_t used2 = used | (1u << p);
+    const uint32_t used2 = used | (1u << p);
     s.moves += 1;
     s.blocks_total += n;
     int gain = n;
@@ -497,37 +559,54 @@ BB_HD void bb_env_apply(BBState& s, int action, const BBTables* T, const BBRewar
         s.max_streak = s.max_streak > s.streak ? s.max_streak : s.streak;
         s.lines_total += lines;
         const int cmul = lines < 4 ? lines : 4;
-        const int smul = s.streak + 1 < 8 ? s.streak + 1 : 8;
-        gain += lines * 80 * cmul * smul;
+        const int smul = s.streak + 1 < 8 ? s.streak + 1 : 8;     // post-increment streak, engine.py:261
+        gain += lines * 80 * cmul * smul;                         // lines*8 "blocks" x 10, engine.py:427
     } else {
         s.streak = 0;
     }
     s.score += gain;
-    uint32_t draws = 0;
-    if (used2 == 7u) {
-        const uint32_t before = s.draw_ctr;
-        s.pieces = bb_deal(s.board, T, seed, env_id, &s.draw_ctr);   // used bits cleared
-        draws = s.draw_ctr - before;
-    } else {
-        s.pieces = (s.pieces & 0x00FFFFFFu) | (used2 << 24);
-    }
-    // game over iff no unused piece has an anchor (engine.py:440-441); masks double as the obs
+    s.pieces = (s.pieces & 0x00FFFFFFu) | (used2 << 24);
+    mv.n = n; mv.lines = lines; mv.gain = gain;
+    mv.needs_deal = used2 == 7u;              // all three placed: regenerate (engine.py:432-437)
+    return mv;
+}
+
+// Second half (after the deal, if any): game over iff no unused piece has an anchor
+// (engine.py:440-441) — the same three valid masks are the next observation's action mask —
+// then the shaped reward, and the vec-env's auto-reset (wrappers.py:96-102).
+BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTables* T, const BBRewardCfg& cfg,
+                       uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o) {
     bb_action_mask(s, T, o.mask);
     const bool over = (o.mask[0] | o.mask[1] | o.mask[2]) == 0ull;
     const int h = bb_holes(s.board), ctr = bb_center(s.board);
-    o.reward = bb_reward(cfg, n, lines, over, h, (int)(s.aux & 0xFFu), ctr, (int)((s.aux >> 8) & 0xFFu));
+    o.reward = bb_reward(cfg, mv.n, mv.lines, over, h, (int)(s.aux & 0xFFu), ctr, (int)((s.aux >> 8) & 0xFFu));
     s.aux = (uint32_t)h | ((uint32_t)ctr << 8) | ((over ? 1u : 0u) << 16);
     o.terminated = over ? 1u : 0u;
-    o.gain = gain;
-    o.info = ((uint32_t)lines << 1) | ((uint32_t)n << 4) | ((uint32_t)(lines > 0 ? (lines < 4 ? lines : 4) : 1) << 8) | (draws << 11);
+    o.gain = mv.gain;
+    o.info = ((uint32_t)mv.lines << 1) | ((uint32_t)mv.n << 4) |
+             ((uint32_t)(mv.lines > 0 ? (mv.lines < 4 ? mv.lines : 4) : 1) << 8) | (draws << 11);
     if (over) {
         o.ep_score = s.score;
         o.ep_len = s.moves;
         if (!(flags & BB_FLAG_NO_AUTO_RESET)) {
-            bb_reset_state(s, T, seed, env_id, flags);
+            bb_reset_state(s, seed, env_id, flags);
             bb_action_mask(s, T, o.mask);
         }
     }
+}
+
+// One env step, sequential form (host build; the kernel composes pre / warp deal / post).
+BB_HD void bb_env_apply(BBState& s, int action, const BBTables* T, const BBRewardCfg& cfg,
+                        uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o) {
+    const BBMove mv = bb_env_pre(s, action, T, o);
+    if (!mv.ok) return;
+    uint32_t draws = 0;
+    if (mv.needs_deal) {
+        const uint32_t before = s.draw_ctr;
+        s.pieces = bb_deal(s.board, T, seed, env_id, &s.draw_ctr);
+        draws = s.draw_ctr - before;
+    }
+    bb_env_post(s, mv, draws, T, cfg, seed, env_id, flags, o);
 }
 
 // k-th valid action (piece-major, then bit order = np.where(mask)[0] order,
@@ -540,7 +619,5 @@ BB_HD int bb_pick_action(const uint64_t m[3], uint32_t word) {
     int p = 0;
     uint64_t w = m[0];
     if (k >= n0) { k -= n0; p = 1; w = m[1]; if (k >= n1) { k -= n1; p = 2; w = m[2]; } }
-    // select the k-th set bit of w
-    for (int i = 0; i < k; ++i) w &= w - 1;
-    return p * 64 + bb_ctz(w);
+    return p * 64 + bb_select(w, k);
 }

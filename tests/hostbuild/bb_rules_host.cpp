@@ -14,7 +14,7 @@ extern "C" {
 
 int64_t bbh_state_size() { return (int64_t)sizeof(BBState); }
 
-uint64_t bbh_valid(uint64_t board, int piece) { init(); return bb_valid(~board, g_tables.mask[piece], g_tables.inb[piece]); }
+uint64_t bbh_valid(uint64_t board, int piece) { init(); return bb_valid(~board, bb_piece(&g_tables, (uint32_t)piece)); }
 uint64_t bbh_clear(uint64_t board, int* lines) { return bb_clear(board, lines); }
 int bbh_holes(uint64_t board) { return bb_holes(board); }
 int bbh_center(uint64_t board) { return bb_center(board); }
@@ -25,9 +25,9 @@ int bbh_solvable(uint64_t board, int p0, int p1, int p2) {
 // 0 reject, 1 accept, 2 hard
 int bbh_solvable_fast(uint64_t board, int p0, int p1, int p2) {
     init();
-    BBTrio t; uint64_t v[3];
-    bb_load_trio(&g_tables, (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16), &t);
-    return bb_solvable_fast(board, &t, v);
+    BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
+    BBItem it;
+    return bb_classify(board, P, &it);
 }
 void bbh_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
     BBPhilox4 r = bb_philox(c0, c1, c2, c3, k0, k1);
@@ -40,7 +40,7 @@ void bbh_reset(BBState* s, int64_t n, uint64_t seed, int64_t env_offset, uint32_
     init();
     for (int64_t i = 0; i < n; ++i) {
         memset(&s[i], 0, sizeof(BBState));
-        bb_reset_state(s[i], &g_tables, seed, (uint64_t)(env_offset + i), flags);
+        bb_reset_state(s[i], seed, (uint64_t)(env_offset + i), flags);
     }
 }
 
@@ -81,9 +81,26 @@ void bbh_step(BBState* s, int64_t n, const int32_t* actions, const double cfg[7]
     }
 }
 
-void bbh_work(long long out[6]) {
+void bbh_work(long long out[7]) {
     out[0] = g_bb_work.valid_calls; out[1] = g_bb_work.fast_accept; out[2] = g_bb_work.fast_reject;
     out[3] = g_bb_work.pack_iters; out[4] = g_bb_work.clear_iters; out[5] = g_bb_work.slow;
+    out[6] = g_bb_work.branches;
+}
+// per-branch evaluation of a HARD item, for checking the branch decomposition the kernel uses
+int bbh_item_plan(uint64_t board, int p0, int p1, int p2, uint32_t* plan) {
+    init();
+    BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
+    BBItem it;
+    const int cls = bb_classify(board, P, &it);
+    *plan = it.plan;
+    return cls;
+}
+int bbh_item_branch(uint64_t board, int p0, int p1, int p2, uint32_t t) {
+    init();
+    BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
+    BBItem it;
+    bb_classify(board, P, &it);
+    return bb_branch(it, P, t) ? 1 : 0;
 }
 void bbh_work_reset() { memset(&g_bb_work, 0, sizeof(g_bb_work)); }
 

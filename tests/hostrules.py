@@ -76,9 +76,9 @@ class HostEnv:
 
 
 def work():
-    out = (C.c_longlong * 6)()
+    out = (C.c_longlong * 7)()
     lib().bbh_work(out)
-    return dict(zip(("valid_calls", "fast_accept", "fast_reject", "pack_iters", "clear_iters", "slow"), list(out)))
+    return dict(zip(("valid_calls", "fast_accept", "fast_reject", "pack_iters", "clear_iters", "slow", "branches"), list(out)))
 
 
 def work_reset():

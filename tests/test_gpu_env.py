@@ -241,7 +241,7 @@ def test_full_size_properties_262144_envs(torch):
     mean_len = s[3] / s[1]
     assert 8 < mean_len < 25, mean_len          # random play: ~14.7 moves per episode
     st = h.get_state()
-    b = st["board"]
+    b = np.ascontiguousarray(st["board"])
     # no full row / column survives a step
     rows = b.view(np.uint8).reshape(n, 8)
     assert not (rows == 0xFF).any()
