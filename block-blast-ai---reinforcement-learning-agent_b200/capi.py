@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libbbgpu.so")
+LIB_PATH = os.environ.get("BBGPU_LIB") or os.path.join(PKG_DIR, "libbbgpu.so")   # BBGPU_LIB: tuning builds only
 
 BB_F32, BB_BF16, BB_U8 = 0, 1, 2
 ENV_RESEED_ON_RESET = 1

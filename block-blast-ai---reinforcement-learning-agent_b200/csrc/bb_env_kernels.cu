@@ -53,73 +53,180 @@ __device__ __forceinline__ uint64_t bb_shfl64(uint64_t v, int src) {
 // ---------------------------------------------------------------------------------------
 // Warp-cooperative trio regeneration (engine.py:155-238).
 //
-// Every lane whose env placed its third piece (`pending`) draws candidate trios from its
-// Philox stream until one is solvable (<= 100 draws).  Most candidates are settled by
-// bb_classify in the owning lane.  The HARD ones (a search is needed) are resolved by the
-// whole warp: the hard lanes are found with a ballot, the 32 lanes are split into equal teams
-// (one per hard item, popc/fns), each team fetches its item from the owner lane with
-// shuffles, every lane evaluates ONE branch of the search (bb_branch), a ballot collects the
-// results, and teams are re-formed for the items still open — so when one heavy item is left
-// all 32 lanes work on it.  The answer is a boolean OR over branches, hence identical to the
-// sequential search whatever the team sizes.
+// An env that placed its third piece must draw candidate trios until one is solvable (at
+// most 100 draws, the last one is kept).  Candidate number d of env e is a pure function
+// Philox(seed, e, d), so the warp evaluates candidates SPECULATIVELY IN PARALLEL instead of
+// one after the other:
+//   1. ballot the pending envs; split the 32 lanes into equal groups, one per pending env;
+//      lane r of a group classifies candidate ctr + r of its env (bb_classify);
+//   2. candidates that need a search (HARD) and come before the group's first provable
+//      ACCEPT are resolved by the whole warp: lanes are re-split into teams, one per hard
+//      item, each lane evaluates one branch of the search one unit at a time, and a ballot
+//      after every unit stops a team as soon as one lane has proved solvability; teams are
+//      re-formed until every item is decided (a lone heavy item ends up with all 32 lanes);
+//   3. every group takes its first solvable candidate IN DRAW ORDER (or consumes all of its
+//      candidates and goes round again), so the accepted trio and the advanced draw counter
+//      are exactly those of the sequential loop.
 // All 32 lanes of the warp must call this (lanes without work pass pending = false).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, const BBTables* T,
-                                                 uint64_t seed, uint64_t env_id, uint32_t& pieces,
-                                                 uint32_t& draw_ctr) {
+#ifdef BB_PROFILE
+#define BB_PROF_DECL long long pf_cls = 0, pf_team = 0, pf_rounds = 0, pf_iters = 0;
+__device__ unsigned long long g_pf_units = 0, g_pf_units_max = 0, g_pf_open_cyc = 0, g_pf_unit_cyc = 0, g_pf_H = 0;
+#define BB_CLK() clock64()
+#else
+#define BB_PROF_DECL
+#endif
+
+// resolve the hard items of this warp; returns, for a lane that passed hard = true, whether
+// its item (board it.b, pieces of `trio`) is solvable
+__device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uint32_t trio, const BBTables* T
+#ifdef BB_PROFILE
+                                              , long long& pf_rounds
+#endif
+                                              ) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    uint32_t attempts = 0;
-    while (__any_sync(FULL, pending)) {
-        BBItem item;
-        item.b = board; item.v[0] = item.v[1] = item.v[2] = 0; item.plan = 0;
-        uint32_t trio = 0;
-        bool hard = false;
-        if (pending) {
-            trio = bb_draw_trio(seed, env_id, draw_ctr);
-            draw_ctr += 1;
-            attempts += 1;
-            pieces = trio;                      // used bits cleared (engine.py:165)
-            BBPiece P[3] = {bb_piece(T, trio & 0xFFu), bb_piece(T, (trio >> 8) & 0xFFu), bb_piece(T, (trio >> 16) & 0xFFu)};
-            const int cls = bb_classify(board, P, &item);
-            if (cls == BB_ACCEPT) pending = false;
-            else if (cls == BB_REJECT) pending = attempts < 100u;     // 100th failure: keep it (engine.py:171-172)
-            else hard = true;
-        }
-        uint32_t next = 0;                      // owner: first branch not yet handed out
-        unsigned hmask = __ballot_sync(FULL, hard);
-        while (hmask) {
-            const int H = __popc(hmask);
-            const int ts = 32 / H;              // team size (>= 1)
-            const int g = lane / ts;            // my team; teams >= H have no item
-            const bool in_team = g < H;
-            const int owner = in_team ? (int)__fns(hmask, 0, g + 1) : lane;
-            BBItem it;
-            it.b = bb_shfl64(item.b, owner);
-            it.v[0] = bb_shfl64(item.v[0], owner);
-            it.v[1] = bb_shfl64(item.v[1], owner);
-            it.v[2] = bb_shfl64(item.v[2], owner);
-            it.plan = __shfl_sync(FULL, item.plan, owner);
-            const uint32_t tr = __shfl_sync(FULL, trio, owner);
-            const uint32_t t = __shfl_sync(FULL, next, owner) + (uint32_t)(lane - g * ts);
+    bool solved = false;
+    uint32_t next = 0;                      // owner: first branch not yet handed out
+    const uint32_t nbr = BB_PLAN_NA(item.plan) + BB_PLAN_NB(item.plan);
+    unsigned hmask = __ballot_sync(FULL, hard);
+    while (hmask) {
+#ifdef BB_PROFILE
+        pf_rounds += 1;
+#endif
+        const int H = __popc(hmask);
+        const int ts = 32 / H;              // team size (>= 1)
+        const int g = lane / ts;            // my team; teams >= H have no item
+        const bool in_team = g < H;
+        const int owner = in_team ? bb_select((uint64_t)hmask, g) : lane;
+        const unsigned team_mask = (ts == 32 ? FULL : ((1u << ts) - 1u)) << ((in_team ? g : 0) * ts);
+        BBItem it;
+        it.b = bb_shfl64(item.b, owner);
+        it.v[0] = bb_shfl64(item.v[0], owner);
+        it.v[1] = bb_shfl64(item.v[1], owner);
+        it.v[2] = bb_shfl64(item.v[2], owner);
+        it.plan = __shfl_sync(FULL, item.plan, owner);
+        const uint32_t tr = __shfl_sync(FULL, trio, owner);
+        const uint32_t t = __shfl_sync(FULL, next, owner) + (uint32_t)(lane - g * ts);
+        const BBPiece p0 = bb_piece(T, tr & 0xFFu), p1 = bb_piece(T, (tr >> 8) & 0xFFu), p2 = bb_piece(T, (tr >> 16) & 0xFFu);
+        BBBranch br;
+        br.bb = 0; br.m0 = 0; br.m1 = 0; br.sel = 0;
+#ifdef BB_PROFILE
+        const long long q0 = BB_CLK();
+#endif
+        if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) br = bb_branch_open(it, p0, p1, p2, t);
+#ifdef BB_PROFILE
+        const long long q1 = BB_CLK();
+        unsigned long long nunits = 0;
+#endif
+        // unit loop: every lane advances its branch by one second-level anchor, then a
+        // ballot tells each team whether one of its lanes has proved the trio solvable
+        unsigned found = 0;                 // bit l set: lane l found a solution
+        for (;;) {
+            const bool work = in_team && !(found & team_mask) && ((br.m0 | br.m1) != 0ull);
+            if (!__any_sync(FULL, work)) break;
             bool f = false;
-            if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) {
-                BBPiece P[3] = {bb_piece(T, tr & 0xFFu), bb_piece(T, (tr >> 8) & 0xFFu), bb_piece(T, (tr >> 16) & 0xFFu)};
-                f = bb_branch(it, P, t);
-            }
-            const unsigned fm = __ballot_sync(FULL, f);
-            if (hard) {
-                const int my = __popc(hmask & ((1u << lane) - 1u));          // index of the team working for me
-                const unsigned tm = (ts == 32 ? FULL : ((1u << ts) - 1u)) << (my * ts);
-                next += (uint32_t)ts;
-                if (fm & tm) { hard = false; pending = false; }               // solvable: accept
-                else if (next >= BB_PLAN_NA(item.plan) + BB_PLAN_NB(item.plan)) {
-                    hard = false;                                             // exhausted: reject
-                    pending = attempts < 100u;
-                }
-            }
-            hmask = __ballot_sync(FULL, hard);
+            if (work) f = bb_branch_unit(br, p0, p1, p2);
+            found |= __ballot_sync(FULL, f);
+#ifdef BB_PROFILE
+            nunits += 1;
+#endif
         }
+#ifdef BB_PROFILE
+        if (lane == 0) {
+            atomicAdd(&g_pf_units, nunits);
+            atomicMax(&g_pf_units_max, nunits);
+            atomicAdd(&g_pf_open_cyc, (unsigned long long)(q1 - q0));
+            atomicAdd(&g_pf_unit_cyc, (unsigned long long)(BB_CLK() - q1));
+            atomicAdd(&g_pf_H, (unsigned long long)H);
+        }
+#endif
+        if (hard) {
+            const int my = __popc(hmask & ((1u << lane) - 1u));          // index of the team working for me
+            const unsigned tm = (ts == 32 ? FULL : ((1u << ts) - 1u)) << (my * ts);
+            next += (uint32_t)ts;
+            if (found & tm) { hard = false; solved = true; }
+            else if (next >= nbr) hard = false;                           // exhausted: not solvable
+        }
+        hmask = __ballot_sync(FULL, hard);
+    }
+    return solved;
+}
+
+__device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, const BBTables* T,
+                                                 uint64_t seed, uint64_t env_id, uint32_t& pieces,
+                                                 uint32_t& draw_ctr
+#ifdef BB_PROFILE
+                                                 , long long& pf_cls, long long& pf_team, long long& pf_rounds, long long& pf_iters
+#endif
+                                                 ) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t attempts = 0;                  // candidates consumed by MY env so far
+    unsigned pmask = __ballot_sync(FULL, pending);
+    while (pmask) {
+#ifdef BB_PROFILE
+        const long long c0 = BB_CLK();
+        pf_iters += 1;
+#endif
+        // 1. groups of w lanes, one group per pending env; lane r classifies candidate ctr + r
+        const int P = __popc(pmask);
+        const int w = 32 / P;
+        const int g = lane / w, r = lane - g * w;
+        const bool in_grp = g < P;
+        const int owner = in_grp ? bb_select((uint64_t)pmask, g) : lane;
+        const unsigned grp_bits = (w == 32 ? FULL : ((1u << w) - 1u));
+        const int shift = (in_grp ? g : 0) * w;
+        const uint64_t ob = bb_shfl64(board, owner);
+        const uint64_t oid = bb_shfl64(env_id, owner);
+        const uint32_t octr = __shfl_sync(FULL, draw_ctr, owner);
+        const uint32_t oatt = __shfl_sync(FULL, attempts, owner);
+        const bool cand = in_grp && (oatt + (uint32_t)r < 100u);
+        BBItem item;
+        item.b = ob; item.v[0] = item.v[1] = item.v[2] = 0; item.plan = 0;
+        uint32_t trio = 0;
+        int cls = BB_REJECT;
+        if (cand) {
+            trio = bb_draw_trio(seed, oid, octr + (uint32_t)r);
+            cls = bb_classify(ob, bb_piece(T, trio & 0xFFu), bb_piece(T, (trio >> 8) & 0xFFu),
+                              bb_piece(T, (trio >> 16) & 0xFFu), &item);
+        }
+        // 2. hard candidates before the group's first provable accept need a search
+        const unsigned amask = __ballot_sync(FULL, cls == BB_ACCEPT);
+        const unsigned ga = (amask >> shift) & grp_bits;
+        const int first_acc = ga ? (__ffs((int)ga) - 1) : w;
+        const bool hard = cand && cls == BB_HARD && r < first_acc;
+#ifdef BB_PROFILE
+        const long long c1 = BB_CLK();
+        pf_cls += c1 - c0;
+#endif
+        const bool solved = bb_warp_solve(hard, item, trio, T
+#ifdef BB_PROFILE
+                                          , pf_rounds
+#endif
+                                          );
+#ifdef BB_PROFILE
+        pf_team += BB_CLK() - c1;
+#endif
+        // 3. first solvable candidate of each group, in draw order
+        const unsigned okmask = __ballot_sync(FULL, cand && (cls == BB_ACCEPT || solved));
+        const unsigned go = (okmask >> shift) & grp_bits;
+        const int nvalid = (int)min((uint32_t)w, 100u - oatt);          // candidates this group really had
+        const int take = go ? __ffs((int)go) : nvalid;                  // draws consumed
+        const bool done = go != 0u || (oatt + (uint32_t)take >= 100u);  // 100th failure: keep it (engine.py:171-172)
+        const uint32_t chosen = __shfl_sync(FULL, trio, (in_grp ? g * w : 0) + take - 1);
+        // hand the verdict to the env's own lane (which may sit in another group)
+        const int my_base = pending ? __popc(pmask & ((1u << lane) - 1u)) * w : 0;
+        const int t_take = __shfl_sync(FULL, take, my_base);
+        const int t_done = __shfl_sync(FULL, (int)done, my_base);
+        const uint32_t t_trio = __shfl_sync(FULL, chosen, my_base);
+        if (pending) {
+            draw_ctr += (uint32_t)t_take;
+            attempts += (uint32_t)t_take;
+            pieces = t_trio;                    // used bits cleared (engine.py:165)
+            pending = !t_done;
+        }
+        pmask = __ballot_sync(FULL, pending);
     }
     return attempts;
 }
@@ -129,7 +236,7 @@ __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, c
 // n_steps back to back with the state held in registers.
 // ---------------------------------------------------------------------------------------
 template <bool RANDOM>
-__global__ void __launch_bounds__(BB_STEP_THREADS)
+__global__ void __launch_bounds__(BB_STEP_THREADS, BB_STEP_MIN_BLOCKS)
 bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actions, int n_steps,
                int32_t* __restrict__ actions_out, float* __restrict__ rewards,
                uint8_t* __restrict__ terminated, uint64_t* __restrict__ mask_out,
@@ -154,6 +261,10 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         o.mask[0] = o.mask[1] = o.mask[2] = 0;
     }
     const int steps = RANDOM ? n_steps : 1;
+    BB_PROF_DECL
+#ifdef BB_PROFILE
+    const long long pf_t0 = BB_CLK();
+#endif
     for (int step = 0; step < steps; ++step) {
         BBMove mv;
         mv.ok = false; mv.needs_deal = false; mv.n = 0; mv.lines = 0; mv.gain = 0;
@@ -168,7 +279,11 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         }
         // all 32 lanes take part in the deal, with or without work of their own
         const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, E.seed, env_id,
-                                            s.pieces, s.draw_ctr);
+                                            s.pieces, s.draw_ctr
+#ifdef BB_PROFILE
+                                            , pf_cls, pf_team, pf_rounds, pf_iters
+#endif
+                                            );
         if (live && mv.ok) {
             bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o);
             if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
@@ -200,6 +315,21 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         }
         const unsigned long long nlive = __popc(__ballot_sync(0xffffffffu, live));
         if ((threadIdx.x & 31) == 0) {
+#ifdef BB_PROFILE
+            const unsigned long long tot = (unsigned long long)(BB_CLK() - pf_t0);
+            atomicAdd(&stats[4], tot);
+            atomicMax(&stats[9], tot);
+            atomicMax(&stats[10], (unsigned long long)pf_rounds);
+            stats[11] = g_pf_units; stats[12] = g_pf_units_max; stats[13] = g_pf_open_cyc; stats[14] = g_pf_unit_cyc; stats[15] = g_pf_H;
+            // histogram of per-warp cycles in bins of 8192 cycles (stats[16..47])
+            atomicAdd(&stats[16 + (tot >> 13 > 31 ? 31 : tot >> 13)], 1ull);
+            // histogram of team rounds per warp (stats[48..63])
+            atomicAdd(&stats[48 + (pf_rounds > 15 ? 15 : pf_rounds)], 1ull);
+            atomicAdd(&stats[5], (unsigned long long)pf_cls);
+            atomicAdd(&stats[6], (unsigned long long)pf_team);
+            atomicAdd(&stats[7], (unsigned long long)pf_rounds);
+            atomicAdd(&stats[8], (unsigned long long)pf_iters);
+#endif
             atomicAdd(&stats[0], nlive * (unsigned long long)n_steps);
             if (st_eps) {
                 atomicAdd(&stats[1], st_eps);

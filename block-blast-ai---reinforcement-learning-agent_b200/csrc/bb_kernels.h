@@ -4,7 +4,12 @@
 #include <stdint.h>
 #include "bb_rules.cuh"
 
+#ifndef BB_STEP_THREADS
 #define BB_STEP_THREADS 128
+#endif
+#ifndef BB_STEP_MIN_BLOCKS
+#define BB_STEP_MIN_BLOCKS 4
+#endif
 
 // device-side view of a batch of envs (SoA of 16-byte words, see bb_rules.cuh BBState)
 struct BBEnvArrays {

@@ -90,12 +90,23 @@ BB_HD uint32_t bb_mulhi(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-// position of the k-th (0-based) set bit of w; k < popcount(w)
+// position of the k-th (0-based) set bit of w; k < popcount(w).  Binary search on popcounts.
 BB_HD int bb_select(uint64_t w, int k) {
 #if defined(__CUDA_ARCH__)
-    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-    const int c = __popc(lo);
-    return k < c ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - c + 1);
+    uint32_t x = (uint32_t)w;
+    int pos = 0;
+    int c = __popc(x);
+    if (k >= c) { k -= c; pos = 32; x = (uint32_t)(w >> 32); }
+    c = __popc(x & 0xFFFFu);
+    if (k >= c) { k -= c; pos += 16; x >>= 16; }
+    c = __popc(x & 0xFFu);
+    if (k >= c) { k -= c; pos += 8; x >>= 8; }
+    c = __popc(x & 0xFu);
+    if (k >= c) { k -= c; pos += 4; x >>= 4; }
+    c = __popc(x & 0x3u);
+    if (k >= c) { k -= c; pos += 2; x >>= 2; }
+    if (k >= (int)(x & 1u)) pos += 1;
+    return pos;
 #else
     for (int i = 0; i < k; ++i) w &= w - 1;
     return __builtin_ctzll(w);
@@ -281,52 +292,20 @@ struct BBItem {
 #define BB_PLAN_NA(p) (((p) >> 8) & 0xFFu)
 #define BB_PLAN_NB(p) (((p) >> 16) & 0xFFu)
 
-// z fits beside some placement of y on b (no clear needed)
-BB_HD bool bb_pack2(uint64_t b, const BBPiece& y, const BBPiece& z) {
-    uint64_t vy = bb_valid(~b, y);
-    BB_WORK(valid_calls, 1);
-    while (vy) {
-        const int a = bb_ctz(vy);
-        vy &= vy - 1;
-        BB_WORK(pack_iters, 1);
-        BB_WORK(valid_calls, 1);
-        if (bb_valid(~(b | (y.pm << a)), z)) return true;
-    }
-    return false;
-}
-
-// exists a CLEARING placement of x on b after which y fits
-BB_HD bool bb_clear_then_fit(uint64_t b, const BBPiece& x, const BBPiece& y) {
-    uint64_t vx = bb_valid(~b, x);
-    BB_WORK(valid_calls, 1);
-    while (vx) {
-        const int a = bb_ctz(vx);
-        vx &= vx - 1;
-        const uint64_t b1 = b | (x.pm << a);
-        BB_WORK(clear_iters, 1);
-        if (bb_any_full(b1)) {
-            BB_WORK(valid_calls, 1);
-            if (bb_valid(~bb_clear_only(b1), y)) return true;
-        }
-    }
-    return false;
-}
-
-// two pieces on board b, any order, clears simulated (engine.py:181-224 at depth 1)
-BB_HD bool bb_solve2(uint64_t b, const BBPiece& j, const BBPiece& k, bool skip_pack) {
-    if (!skip_pack && bb_pack2(b, j, k)) return true;
-    const BBLines L = bb_lines(b);
-    if ((bb_row_within(L, (int)BB_META_MAXROW(j.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(j.meta))) &&
-        bb_clear_then_fit(b, j, k)) return true;
-    if ((bb_row_within(L, (int)BB_META_MAXROW(k.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(k.meta))) &&
-        bb_clear_then_fit(b, k, j)) return true;
-    return false;
+// piece i of three without dynamic indexing (keeps everything in registers on the device)
+BB_HD BBPiece bb_pick3(const BBPiece& p0, const BBPiece& p1, const BBPiece& p2, int i) {
+    BBPiece r;
+    r.pm = i == 0 ? p0.pm : (i == 1 ? p1.pm : p2.pm);
+    r.inb = i == 0 ? p0.inb : (i == 1 ? p1.inb : p2.inb);
+    r.offs = i == 0 ? p0.offs : (i == 1 ? p1.offs : p2.offs);
+    r.meta = i == 0 ? p0.meta : (i == 1 ? p1.meta : p2.meta);
+    return r;
 }
 
 // fact (C) for three pieces: can the two largest per-line contributions complete any line?
-BB_HD bool bb_clear_reachable(uint64_t b, const BBPiece P[3]) {
-    const int r0 = (int)BB_META_MAXROW(P[0].meta), r1 = (int)BB_META_MAXROW(P[1].meta), r2 = (int)BB_META_MAXROW(P[2].meta);
-    const int c0 = (int)BB_META_MAXCOL(P[0].meta), c1 = (int)BB_META_MAXCOL(P[1].meta), c2 = (int)BB_META_MAXCOL(P[2].meta);
+BB_HD bool bb_clear_reachable(uint64_t b, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2) {
+    const int r0 = (int)BB_META_MAXROW(p0.meta), r1 = (int)BB_META_MAXROW(p1.meta), r2 = (int)BB_META_MAXROW(p2.meta);
+    const int c0 = (int)BB_META_MAXCOL(p0.meta), c1 = (int)BB_META_MAXCOL(p1.meta), c2 = (int)BB_META_MAXCOL(p2.meta);
     const int rmin = r0 < r1 ? (r0 < r2 ? r0 : r2) : (r1 < r2 ? r1 : r2);
     const int cmin = c0 < c1 ? (c0 < c2 ? c0 : c2) : (c1 < c2 ? c1 : c2);
     const int rt = r0 + r1 + r2 - rmin, ct = c0 + c1 + c2 - cmin;
@@ -337,12 +316,12 @@ BB_HD bool bb_clear_reachable(uint64_t b, const BBPiece P[3]) {
 
 // Cheap classification of (board, trio): ACCEPT / REJECT when provable with a handful of
 // valid-mask evaluations, else HARD with the item's branch plan filled in.
-BB_HD int bb_classify(uint64_t b, const BBPiece P[3], BBItem* it) {
+BB_HD int bb_classify(uint64_t b, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2, BBItem* it) {
     const uint64_t e = ~b;
     it->b = b;
-    it->v[0] = bb_valid(e, P[0]);
-    it->v[1] = bb_valid(e, P[1]);
-    it->v[2] = bb_valid(e, P[2]);
+    it->v[0] = bb_valid(e, p0);
+    it->v[1] = bb_valid(e, p1);
+    it->v[2] = bb_valid(e, p2);
     BB_WORK(valid_calls, 3);
     const int n0 = bb_popc(it->v[0]), n1 = bb_popc(it->v[1]), n2 = bb_popc(it->v[2]);
     uint32_t nA = 0, order = 0;
@@ -352,14 +331,16 @@ BB_HD int bb_classify(uint64_t b, const BBPiece P[3], BBItem* it) {
         if (n1 < n0 && n1 <= n2) { x = 1; y = 0; }
         else if (n2 < n0 && n2 < n1) { x = 2; z = 0; }
         const int ny = (y == 0 ? n0 : (y == 1 ? n1 : n2)), nz = (z == 0 ? n0 : (z == 1 ? n1 : n2));
-        if (nz < ny) { const int s = y; y = z; z = s; }
-        const uint64_t b1 = b | (P[x].pm << bb_ctz(it->v[x]));
-        const uint64_t vy = bb_valid(~b1, P[y]);
+        if (nz < ny) { const int s_ = y; y = z; z = s_; }
+        const BBPiece px = bb_pick3(p0, p1, p2, x), py = bb_pick3(p0, p1, p2, y), pz = bb_pick3(p0, p1, p2, z);
+        const uint64_t vx = x == 0 ? it->v[0] : (x == 1 ? it->v[1] : it->v[2]);
+        const uint64_t b1 = b | (px.pm << bb_ctz(vx));
+        const uint64_t vy = bb_valid(~b1, py);
         BB_WORK(valid_calls, 1);
         if (vy) {
             // lowest and highest anchor of y: two cheap tries
             BB_WORK(valid_calls, 1);
-            if (bb_valid(~(b1 | (P[y].pm << bb_ctz(vy))), P[z])) return BB_ACCEPT;
+            if (bb_valid(~(b1 | (py.pm << bb_ctz(vy))), pz)) return BB_ACCEPT;
             const int ah = 63 - (int)
 #if defined(__CUDA_ARCH__)
                 __clzll((long long)vy);
@@ -367,49 +348,105 @@ BB_HD int bb_classify(uint64_t b, const BBPiece P[3], BBItem* it) {
                 __builtin_clzll(vy);
 #endif
             BB_WORK(valid_calls, 1);
-            if (bb_valid(~(b1 | (P[y].pm << ah)), P[z])) return BB_ACCEPT;
+            if (bb_valid(~(b1 | (py.pm << ah)), pz)) return BB_ACCEPT;
         }
         nA = (uint32_t)(x == 0 ? n0 : (x == 1 ? n1 : n2));
         order = (uint32_t)x | ((uint32_t)y << 2) | ((uint32_t)z << 4);
     }
     // stage B is only worth exploring if some line can be completed at all (fact C)
-    const uint32_t nB = bb_clear_reachable(b, P) ? (uint32_t)(n0 + n1 + n2) : 0u;
+    const uint32_t nB = bb_clear_reachable(b, p0, p1, p2) ? (uint32_t)(n0 + n1 + n2) : 0u;
     it->plan = order | (nA << 8) | (nB << 16);
     if (nA + nB == 0) return BB_REJECT;
     return BB_HARD;
 }
 
-// one branch of a HARD item; t in [0, nA + nB)
-BB_HD bool bb_branch(const BBItem& it, const BBPiece P[3], uint32_t t) {
+// A branch = one first-level placement already applied (board bb, cleared if it completed a
+// line) plus up to two second-level scans, processed one anchor ("unit") at a time:
+//   phase 0: piece f0 at each anchor of m0, then piece f1 must fit
+//   phase 1: piece f1 at each anchor of m1, then piece f0 must fit
+// A phase in "always" mode tests the leaf for every anchor; otherwise only for anchors whose
+// placement completes a line (the no-clear case is covered elsewhere: fact P).
+struct BBBranch {
+    uint64_t bb, m0, m1;
+    uint32_t sel;      // bits 0-1 f0, bits 2-3 f1, bit 4 phase-0 always, bit 5 phase-1 always
+};
+
+BB_HD bool bb_can_complete_line(const BBLines& L, const BBPiece& p) {
+    return bb_row_within(L, (int)BB_META_MAXROW(p.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(p.meta));
+}
+
+// open branch t of a HARD item, t in [0, nA + nB)
+BB_HD BBBranch bb_branch_open(const BBItem& it, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2, uint32_t t) {
     BB_WORK(branches, 1);
+    BBBranch br;
     const uint32_t nA = BB_PLAN_NA(it.plan);
     if (t < nA) {
         const int x = (int)(it.plan & 3u), y = (int)((it.plan >> 2) & 3u), z = (int)((it.plan >> 4) & 3u);
-        const uint64_t b1 = it.b | (P[x].pm << bb_select(it.v[x], (int)t));
-        BB_WORK(valid_calls, 1);
-        if (!bb_valid(~b1, P[z])) return false;       // z must still fit at all
-        return bb_pack2(b1, P[y], P[z]);
+        const uint64_t vx = x == 0 ? it.v[0] : (x == 1 ? it.v[1] : it.v[2]);
+        const BBPiece px = bb_pick3(p0, p1, p2, x);
+        const uint64_t b1 = it.b | (px.pm << bb_select(vx, (int)t));
+        br.bb = bb_any_full(b1) ? bb_clear_only(b1) : b1;
+        BB_WORK(valid_calls, 2);
+        // z must still fit beside x at all, else no packing goes through this anchor
+        br.m0 = bb_valid(~br.bb, bb_pick3(p0, p1, p2, z)) ? bb_valid(~br.bb, bb_pick3(p0, p1, p2, y)) : 0ull;
+        br.m1 = 0ull;
+        br.sel = (uint32_t)y | ((uint32_t)z << 2) | 16u;
+        return br;
     }
     int k = (int)(t - nA);
     int i = 0;
     const int n0 = bb_popc(it.v[0]), n1 = bb_popc(it.v[1]);
     if (k >= n0) { k -= n0; i = 1; if (k >= n1) { k -= n1; i = 2; } }
     const int j = i == 0 ? 1 : 0, l = i == 2 ? 1 : 2;
-    const uint64_t b1 = it.b | (P[i].pm << bb_select(it.v[i], k));
-    if (bb_any_full(b1)) return bb_solve2(bb_clear_only(b1), P[j], P[l], false);
-    // nothing cleared: a packing of the other two on b1 is stage A's business (or impossible),
-    // so only a clearing second placement can help
-    return bb_solve2(b1, P[j], P[l], true);
+    const uint64_t vi = i == 0 ? it.v[0] : (i == 1 ? it.v[1] : it.v[2]);
+    const BBPiece pi = bb_pick3(p0, p1, p2, i);
+    const uint64_t b1 = it.b | (pi.pm << bb_select(vi, k));
+    const bool full1 = bb_any_full(b1);
+    br.bb = full1 ? bb_clear_only(b1) : b1;
+    const BBPiece pj = bb_pick3(p0, p1, p2, j), pl = bb_pick3(p0, p1, p2, l);
+    const BBLines L = bb_lines(br.bb);
+    BB_WORK(valid_calls, 2);
+    // first placement cleared a line: everything about (j,l) is open; j first covers the
+    // packings of both orders, l first matters only when l itself clears.  Nothing cleared:
+    // a packing of (j,l) beside i is stage A's business, only clearing placements matter.
+    br.m0 = (full1 || bb_can_complete_line(L, pj)) ? bb_valid(~br.bb, pj) : 0ull;
+    br.m1 = bb_can_complete_line(L, pl) ? bb_valid(~br.bb, pl) : 0ull;
+    br.sel = (uint32_t)j | ((uint32_t)l << 2) | (full1 ? 16u : 0u);
+    return br;
 }
 
-// sequential driver (host build, reset path): same branches, in index order
+// process one unit of an open branch (precondition: (m0 | m1) != 0); true = trio solvable
+BB_HD bool bb_branch_unit(BBBranch& br, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2) {
+    const bool ph = br.m0 == 0ull;
+    uint64_t m = ph ? br.m1 : br.m0;
+    const int a = bb_ctz(m);
+    m &= m - 1;
+    if (ph) br.m1 = m; else br.m0 = m;
+    const int fi = (int)((br.sel >> (ph ? 2 : 0)) & 3u), si = (int)((br.sel >> (ph ? 0 : 2)) & 3u);
+    const uint64_t pm = fi == 0 ? p0.pm : (fi == 1 ? p1.pm : p2.pm);
+    const uint64_t b2 = br.bb | (pm << a);
+    const bool full = bb_any_full(b2);
+    BB_WORK(clear_iters, 1);
+    if (!full && !((br.sel >> (ph ? 5 : 4)) & 1u)) return false;
+    BB_WORK(valid_calls, 1);
+    return bb_valid(~(full ? bb_clear_only(b2) : b2), bb_pick3(p0, p1, p2, si)) != 0ull;
+}
+
+// sequential drivers (host build): same branches and units, in index order
+BB_HD bool bb_branch(const BBItem& it, const BBPiece P[3], uint32_t t) {
+    BBBranch br = bb_branch_open(it, P[0], P[1], P[2], t);
+    while (br.m0 | br.m1)
+        if (bb_branch_unit(br, P[0], P[1], P[2])) return true;
+    return false;
+}
+
 BB_HD bool bb_solvable(uint64_t b, const BBTables* T, uint32_t trio) {
     BBPiece P[3];
     P[0] = bb_piece(T, trio & 0xFFu);
     P[1] = bb_piece(T, (trio >> 8) & 0xFFu);
     P[2] = bb_piece(T, (trio >> 16) & 0xFFu);
     BBItem it;
-    const int f = bb_classify(b, P, &it);
+    const int f = bb_classify(b, P[0], P[1], P[2], &it);
     if (f == BB_ACCEPT) { BB_WORK(fast_accept, 1); return true; }
     if (f == BB_REJECT) { BB_WORK(fast_reject, 1); return false; }
     BB_WORK(slow, 1);

@@ -27,7 +27,7 @@ int bbh_solvable_fast(uint64_t board, int p0, int p1, int p2) {
     init();
     BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
     BBItem it;
-    return bb_classify(board, P, &it);
+    return bb_classify(board, P[0], P[1], P[2], &it);
 }
 void bbh_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
     BBPhilox4 r = bb_philox(c0, c1, c2, c3, k0, k1);
@@ -91,7 +91,7 @@ int bbh_item_plan(uint64_t board, int p0, int p1, int p2, uint32_t* plan) {
     init();
     BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
     BBItem it;
-    const int cls = bb_classify(board, P, &it);
+    const int cls = bb_classify(board, P[0], P[1], P[2], &it);
     *plan = it.plan;
     return cls;
 }
@@ -99,7 +99,7 @@ int bbh_item_branch(uint64_t board, int p0, int p1, int p2, uint32_t t) {
     init();
     BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
     BBItem it;
-    bb_classify(board, P, &it);
+    bb_classify(board, P[0], P[1], P[2], &it);
     return bb_branch(it, P, t) ? 1 : 0;
 }
 void bbh_work_reset() { memset(&g_bb_work, 0, sizeof(g_bb_work)); }
