@@ -1,0 +1,143 @@
+"""Policy/value network with the reference's architecture and state_dict layout.
+
+Mirror of ``BlockBlastNetwork`` (reference src/models/network.py:34-271): 4 input planes
+(board + 3 piece masks) -> conv 64 -> conv 128 + residual block -> conv 128 + residual block
+-> FC 8192->512->256 (ReLU, Dropout 0.1) -> policy head 256->256->192, value head 256->128->1;
+5,290,113 parameters.  Module and parameter names are the reference's, so checkpoints written
+by either side load in the other (``network_state_dict``, src/agents/ppo.py:425-439).
+
+The CNN body stays PyTorch (north_star).  What is replaced is the categorical head:
+``get_action_and_value`` without gradients (rollout / evaluation) runs the fused K3 kernel
+(-inf masking + softmax + sample/argmax + log-prob + masked entropy, network.py:172-262);
+with gradients (PPO update) the same maths is expressed in torch ops so autograd applies.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import capi
+
+
+class ResidualBlock(nn.Module):
+    """conv-bn-relu-conv-bn + skip, relu (reference network.py:14-31)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.conv2 = nn.Conv2d(channels, channels, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(channels)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + x)
+
+
+def _pack_mask_planes(mask_dense):
+    """(B,192) 0/1 tensor -> int64 [3,B] bit planes (bit = row*8+col), on the mask's device."""
+    b = mask_dense.shape[0]
+    bits = (mask_dense != 0).reshape(b, 3, 8, 8).to(torch.int64)
+    byte_w = (2 ** torch.arange(8, device=mask_dense.device, dtype=torch.int64)).view(1, 1, 1, 8)
+    rows = (bits * byte_w).sum(-1)                                   # (B,3,8) row bytes 0..255
+    shifts = (8 * torch.arange(8, device=mask_dense.device, dtype=torch.int64)).view(1, 1, 8)
+    hi_fix = rows << shifts                                          # row 7 lands in the sign bit: two's complement is fine
+    return hi_fix.sum(-1).t().contiguous()                           # wraps modulo 2**64
+
+
+class BlockBlastNetwork(nn.Module):
+    def __init__(self, board_size=8, num_pieces=3, conv_channels=(64, 128, 128), fc_hidden=(512, 256),
+                 action_space_size=192, use_residual=True, use_batch_norm=True):
+        super().__init__()
+        self.board_size, self.num_pieces, self.action_space_size = board_size, num_pieces, action_space_size
+        layers, cin = [], 1 + num_pieces
+        for i, cout in enumerate(conv_channels):
+            layers.append(nn.Conv2d(cin, cout, 3, padding=1))
+            if use_batch_norm:
+                layers.append(nn.BatchNorm2d(cout))
+            layers.append(nn.ReLU())
+            if use_residual and i > 0:
+                layers.append(ResidualBlock(cout))
+            cin = cout
+        self.conv_encoder = nn.Sequential(*layers)
+        fc, fin = [], conv_channels[-1] * board_size * board_size
+        for h in fc_hidden:
+            fc += [nn.Linear(fin, h), nn.ReLU(), nn.Dropout(0.1)]
+            fin = h
+        self.fc_encoder = nn.Sequential(*fc)
+        self.policy_head = nn.Sequential(nn.Linear(fin, 256), nn.ReLU(), nn.Linear(256, action_space_size))
+        self.value_head = nn.Sequential(nn.Linear(fin, 128), nn.ReLU(), nn.Linear(128, 1))
+        self._sample_calls = 0
+        self.sample_seed = 0
+        for m in self.modules():                      # reference network.py:122-133
+            if isinstance(m, (nn.Linear, nn.Conv2d)):
+                nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    # ---------------------------------------------------------------- body
+    def trunk(self, x):
+        """x: (B,4,8,8) = cat([board, pieces]) (network.py:152-158) -> (raw logits (B,192), value (B,))."""
+        x = self.conv_encoder(x)
+        x = self.fc_encoder(x.flatten(1))
+        return self.policy_head(x), self.value_head(x).squeeze(-1)
+
+    @staticmethod
+    def _nchw(board, pieces):
+        if board.dim() == 3:
+            board = board.unsqueeze(1)
+        return torch.cat([board, pieces], dim=1)
+
+    def forward(self, board, pieces, action_mask=None):
+        logits, value = self.trunk(self._nchw(board, pieces))
+        if action_mask is not None:                    # network.py:172-180
+            logits = logits.masked_fill(~action_mask.bool(), float("-inf"))
+        return logits, value
+
+    def get_value(self, board, pieces):
+        return self.forward(board, pieces)[1]
+
+    # ---------------------------------------------------------------- masked categorical head
+    def head_from_logits(self, raw_logits, mask_planes, action=None, deterministic=False, need_entropy=True):
+        """K3 on raw (unmasked) logits and packed mask planes int64 [3,B]; no autograd."""
+        n = raw_logits.shape[0]
+        logits = raw_logits.detach()
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        logits = logits.contiguous()
+        logp = torch.empty(n, dtype=torch.float32, device=logits.device)
+        ent = torch.empty(n, dtype=torch.float32, device=logits.device) if need_entropy else None
+        if action is None:
+            act = torch.empty(n, dtype=torch.int32, device=logits.device)
+            self._sample_calls += 1
+            capi.masked_sample(logits, mask_planes, mask_planes.stride(0), self.sample_seed, self._sample_calls,
+                               1 if deterministic else 0, act, logp, ent)
+        else:
+            act = action.to(torch.int32).contiguous()
+            capi.masked_sample(logits, mask_planes, mask_planes.stride(0), 0, 0, 2, act, logp, ent)
+        return act, logp, ent
+
+    def get_action_and_value(self, board, pieces, action_mask, action=None, deterministic=False):
+        """network.py:184-230.  Returns (action int64, log_prob, entropy, value)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and action is not None:
+            return self.evaluate_actions(self._nchw(board, pieces), action_mask, action)
+        logits, value = self.trunk(self._nchw(board, pieces))
+        if not logits.is_cuda:
+            raise capi.BBGpuError("BlockBlastNetwork's masked head runs on CUDA only (no CPU fallback)")
+        planes = _pack_mask_planes(action_mask)
+        act, logp, ent = self.head_from_logits(logits, planes, action, deterministic)
+        return act.long(), logp, ent, value
+
+    def evaluate_actions(self, x_nchw, action_mask, action):
+        """Differentiable log-prob / masked entropy of given actions (PPO update,
+        src/agents/ppo.py:366-369 -> network.py:210-262), same formulas as K3."""
+        logits, value = self.trunk(x_nchw)
+        logits = logits.float()
+        valid = action_mask.bool()
+        probs = F.softmax(logits.masked_fill(~valid, float("-inf")), dim=-1)
+        eps = torch.finfo(torch.float32).eps
+        pn = probs / probs.sum(-1, keepdim=True)
+        logp = torch.log(pn.clamp(eps, 1 - eps)).gather(1, action.long().unsqueeze(1)).squeeze(1)
+        q = probs / probs.sum(-1, keepdim=True).clamp(min=1e-10)      # probs already 0 where masked
+        ent = -(q * torch.log(q.clamp(min=1e-10)) * valid).sum(-1)
+        return action, logp, ent, value

@@ -1,0 +1,192 @@
+"""PPO agent with action masking — the reference's ``PPOConfig`` / ``PPOAgent`` interface
+(src/agents/ppo.py:26-449) on the device-resident path.
+
+Collect: packed obs -> K2 (planes) -> CNN (PyTorch) -> K3 (masked sample + log-prob) -> K1
+(env step), nothing leaves HBM.  Update: K4 GAE, whole-buffer advantage normalisation,
+clipped surrogate + 0.5*MSE value loss + 0.01*entropy (ppo.py:372-392), grad-norm clip 0.5,
+Adam(eps=1e-5).  With torch.distributed initialised every optimiser step all-reduces the
+gradients in one flat NCCL bucket (dist.py); BatchNorm statistics stay per GPU (the
+single-device reference has nothing to synchronise them with).
+"""
+from dataclasses import dataclass, field, fields
+from typing import Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import capi, dist
+from .network import BlockBlastNetwork, _pack_mask_planes
+from .rollout import RolloutBuffer  # noqa: F401  (re-export, as in the reference module)
+
+
+@dataclass
+class PPOConfig:
+    """Field names and defaults of the reference (ppo.py:26-46); ``precision`` is ours."""
+    learning_rate: float = 3e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_epsilon: float = 0.2
+    entropy_coef: float = 0.01
+    value_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    num_epochs: int = 10
+    batch_size: int = 64
+    conv_channels: Tuple[int, ...] = (64, 128, 128)
+    fc_hidden: Tuple[int, ...] = (512, 256)
+    precision: str = "fp32"          # "fp32" (reference numerics) | "bf16" (autocast, channels_last)
+
+    def to_dict(self):
+        return {f.name: getattr(self, f.name) for f in fields(self)}
+
+    @classmethod
+    def from_dict(cls, data):
+        names = {f.name for f in fields(cls)}
+        return cls(**{k: v for k, v in data.items() if k in names})
+
+
+class PPOAgent:
+    def __init__(self, config=None, device=None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise capi.BBGpuError("PPOAgent needs a CUDA device (no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.config = config or PPOConfig()
+        self.training = True
+        self.network = BlockBlastNetwork(conv_channels=tuple(self.config.conv_channels),
+                                         fc_hidden=tuple(self.config.fc_hidden)).to(self.device)
+        if self.config.precision == "bf16":
+            self.network = self.network.to(memory_format=torch.channels_last)
+        dist.broadcast_module(self.network)
+        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5)
+        self.scheduler = None
+        self.bucket = dist.FlatGradBucket(self.network.parameters())
+
+    # ------------------------------------------------------------------ helpers
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.config.precision == "bf16")
+
+    def _trunk(self, x):
+        if self.config.precision == "bf16":
+            x = x.contiguous(memory_format=torch.channels_last)
+        with self._autocast():
+            logits, value = self.network.trunk(x)
+        return logits, value.float()
+
+    def _obs_to_nchw(self, obs):
+        """obs dict -> ((B,4,8,8) f32, mask planes int64 [3,B]) on the device.  Accepts the packed
+        protocol ('board' int64[N], 'pieces' int32[N], 'mask' int64[3,N]) or dense arrays."""
+        dev = self.device
+        if "mask" in obs and isinstance(obs["board"], torch.Tensor) and obs["board"].dtype == torch.int64:
+            n = obs["board"].shape[0]
+            x = torch.empty((n, 4, 8, 8), dtype=torch.float32, device=dev)
+            capi.unpack_obs(obs["board"], obs["pieces"], obs["mask"], obs["mask"].stride(0), obs=x, n=n)
+            return x, obs["mask"]
+        if "nchw" in obs:
+            x = obs["nchw"]
+        else:
+            b = torch.as_tensor(np.asarray(obs["board"]) if not isinstance(obs["board"], torch.Tensor) else obs["board"]).to(dev).float()
+            p = torch.as_tensor(np.asarray(obs["pieces"]) if not isinstance(obs["pieces"], torch.Tensor) else obs["pieces"]).to(dev).float()
+            x = torch.cat([b.unsqueeze(1), p], dim=1)
+        planes = None
+        if "action_mask" in obs:
+            m = obs["action_mask"]
+            m = m if isinstance(m, torch.Tensor) else torch.as_tensor(np.asarray(m))
+            planes = _pack_mask_planes(m.to(dev))
+        return x, planes
+
+    # ------------------------------------------------------------------ acting
+    @torch.no_grad()
+    def act(self, obs, deterministic=False):
+        """Device fast path: returns (actions int32, log_probs, values) as CUDA tensors."""
+        x, planes = self._obs_to_nchw(obs)
+        logits, value = self._trunk(x)
+        act, logp, _ = self.network.head_from_logits(logits, planes, None, deterministic, need_entropy=False)
+        return act, logp, value
+
+    def select_actions(self, observations, deterministic=False):
+        """ppo.py:291-319: numpy in, numpy out."""
+        act, logp, value = self.act(observations, deterministic)
+        return act.cpu().numpy().astype(np.int64), logp.cpu().numpy(), value.cpu().numpy()
+
+    def select_action(self, observation, deterministic=False):
+        """ppo.py:261-289 (single observation)."""
+        obs = {k: (v.unsqueeze(0) if isinstance(v, torch.Tensor) else np.asarray(v)[None]) for k, v in observation.items()
+               if k in ("board", "pieces", "action_mask")}
+        x, planes = self._obs_to_nchw(obs)
+        with torch.no_grad():
+            logits, value = self._trunk(x)
+            act, logp, ent = self.network.head_from_logits(logits, planes, None, deterministic)
+        return int(act.item()), {"log_prob": float(logp.item()), "entropy": float(ent.item()), "value": float(value.item())}
+
+    @torch.no_grad()
+    def values(self, obs):
+        x, _ = self._obs_to_nchw({k: v for k, v in obs.items() if k != "action_mask"})
+        return self._trunk(x)[1]
+
+    def get_values(self, observations):
+        """ppo.py:321-328."""
+        return self.values(observations).cpu().numpy()
+
+    # ------------------------------------------------------------------ update
+    def update(self, buffer, last_values):
+        """ppo.py:330-423.  Returns the reference's metric dict."""
+        cfg = self.config
+        buffer.compute_returns_and_advantages(last_values, cfg.gamma, cfg.gae_lambda)
+        sums = torch.zeros(6, dtype=torch.float64, device=self.device)
+        n_updates = 0
+        self.bucket.rebind()
+        for _ in range(cfg.num_epochs):
+            for obs, mask, actions, old_logp, adv, ret in buffer.iter_minibatches(cfg.batch_size):
+                if cfg.precision == "bf16":
+                    obs = obs.contiguous(memory_format=torch.channels_last)
+                with self._autocast():
+                    _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
+                values = values.float()
+                ratio = torch.exp(new_logp - old_logp)
+                surr1 = ratio * adv
+                surr2 = torch.clamp(ratio, 1 - cfg.clip_epsilon, 1 + cfg.clip_epsilon) * adv
+                policy_loss = -torch.min(surr1, surr2).mean()
+                value_loss = F.mse_loss(values, ret)
+                entropy_loss = -entropy.mean()
+                loss = policy_loss + cfg.value_coef * value_loss + cfg.entropy_coef * entropy_loss
+                self.bucket.zero()
+                loss.backward()
+                self.bucket.all_reduce_mean()                      # C1: one flat NCCL all-reduce
+                nn.utils.clip_grad_norm_(self.network.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+                with torch.no_grad():
+                    approx_kl = ((ratio - 1) - torch.log(ratio)).mean()
+                    clip_frac = ((ratio - 1).abs() > cfg.clip_epsilon).float().mean()
+                    sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.mean().detach(),
+                                         loss.detach(), approx_kl, clip_frac]).double()
+                n_updates += 1
+        s = (sums / max(n_updates, 1)).cpu().tolist()
+        return {"policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
+                "approx_kl": s[4], "clip_fraction": s[5]}
+
+    # ------------------------------------------------------------------ persistence / modes
+    def save(self, path):
+        """Same keys as ppo.py:425-431 so the reference's evaluate.py / GUI can load it."""
+        cfgd = {k: v for k, v in self.config.to_dict().items() if k != "precision"}
+        torch.save({"network_state_dict": self.network.state_dict(),
+                    "optimizer_state_dict": self.optimizer.state_dict(), "config": cfgd}, path)
+
+    def load(self, path):
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        self.network.load_state_dict(ck["network_state_dict"])
+        if "optimizer_state_dict" in ck:
+            self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+        if "config" in ck:
+            self.config = PPOConfig.from_dict({**ck["config"], "precision": self.config.precision})
+        self.bucket.rebind()
+
+    def train(self):
+        self.training = True
+        self.network.train()
+
+    def eval(self):
+        self.training = False
+        self.network.eval()

@@ -1,0 +1,210 @@
+"""GPU tests of the drop-in classes: VectorizedBlockBlastEnv / BlockBlastEnv (reference
+tests/test_environment.py KATs), RolloutBuffer (vs the oracle's GAE / normalisation), PPOAgent
+(update metrics vs an independent computation) and a short end-to-end training run."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def test_vectorized_env_api_shapes_and_codec(torch):
+    from bbgpu.vec_env import VectorizedBlockBlastEnv, BlockBlastEnv
+    v = VectorizedBlockBlastEnv(num_envs=4, seed=42)
+    assert v.num_envs == 4 and v.action_space.n == 192 and v.single_action_space.n == 192
+    obs, infos = v.reset()
+    assert obs["board"].shape == (4, 8, 8) and obs["board"].dtype == np.float32
+    assert obs["pieces"].shape == (4, 3, 8, 8) and obs["pieces"].dtype == np.float32
+    assert obs["action_mask"].shape == (4, 192) and obs["action_mask"].dtype == np.int8
+    assert len(infos) == 4 and infos[0]["score"] == 0
+    masks = v.get_action_masks()
+    assert masks.shape == (4, 192) and masks.dtype == bool and np.array_equal(masks, obs["action_mask"].astype(bool))
+    a = v.sample_valid_actions()
+    assert a.shape == (4,) and all(masks[i, a[i]] for i in range(4))
+    obs2, rew, term, trunc, infos = v.step(a)
+    assert rew.shape == (4,) and rew.dtype == np.float32 and term.dtype == bool and not trunc.any()
+    assert (obs2["board"].sum(axis=(1, 2)) > 0).all()
+    # invalid action: negative reward, flagged, state untouched (tests/test_environment.py:100-114)
+    bad = np.array([int(np.where(~v.get_action_masks()[i])[0][0]) for i in range(4)])
+    before = v.handle.get_state().tobytes()
+    _, rew, term, _, _ = v.step(bad)
+    assert (rew == -10.0).all() and not term.any() and v.handle.get_state().tobytes() == before
+    v.close()
+    e = BlockBlastEnv(seed=3)
+    assert (e.BOARD_SIZE, e.NUM_PIECES_PER_TURN, e.ACTION_SPACE_SIZE) == (8, 3, 192)
+    assert e._action_to_move(0) == (0, 0, 0) and e._action_to_move(64) == (1, 0, 0) and e._action_to_move(128) == (2, 0, 0)
+    assert e._move_to_action(0, 7, 7) == 63
+    e.close()
+
+
+def test_single_env_matches_python_oracle_episode(torch):
+    """BlockBlastEnv (no auto-reset) against oracle.Env fed the same Philox trio stream."""
+    from bbgpu import philox
+    from bbgpu.vec_env import BlockBlastEnv
+    from oracle import bb_oracle as O
+    seed = 21
+    stream = iter(philox.candidate_trios(seed, [0], 512)[0])
+    ora = O.Env(draw=lambda: next(stream))
+    env = BlockBlastEnv(seed=seed)           # constructor deals draw 0, like the oracle's
+    rs = np.random.RandomState(0)
+    done = False
+    steps = 0
+    while not done and steps < 200:
+        va = ora.valid_actions()
+        assert env.get_valid_actions() == va
+        a = int(va[rs.randint(len(va))]) if rs.rand() > 0.1 else int(rs.randint(0, 192))
+        oo, orw, od, _, oi = ora.step(a)
+        go, grw, gd, gt, gi = env.step(a)
+        assert np.float32(orw) == np.float32(grw) and od == gd and gt is False
+        assert np.array_equal(oo["board"], go["board"]) and np.array_equal(oo["pieces"], go["pieces"])
+        assert np.array_equal(oo["action_mask"], go["action_mask"])
+        for k in ("score", "moves", "lines_cleared", "max_combo", "blocks_placed", "holes", "invalid_action"):
+            assert oi[k] == gi[k], k
+        assert abs(oi["board_fill"] - gi["board_fill"]) < 1e-12
+        done = od
+        steps += 1
+    assert done
+    # after game over every action is rejected with -10 (block_blast_env.py:240-245)
+    _, r, t, _, info = env.step(0)
+    assert r == -10.0 and t is False and info["invalid_action"]
+    env.close()
+
+
+def test_rollout_buffer_gae_and_samples(torch):
+    from bbgpu.rollout import RolloutBuffer
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    from oracle import bb_oracle as O
+    T, N = 12, 96
+    venv = VectorizedBlockBlastEnv(N, seed=5, output="packed")
+    obs, _ = venv.reset()
+    buf = RolloutBuffer(T, N)
+    rs = np.random.RandomState(1)
+    kept = []
+    for t in range(T):
+        act = venv.sample_valid_actions()
+        lp = torch.from_numpy(rs.randn(N).astype(np.float32)).cuda()
+        val = torch.from_numpy(rs.randn(N).astype(np.float32)).cuda()
+        kept.append((obs["board"].cpu().numpy().copy(), obs["pieces"].cpu().numpy().copy(), obs["mask"].cpu().numpy().copy()))
+        buf.add_obs(obs, act, lp, val)
+        obs, rew, term, trunc, infos = venv.step(act)
+        buf.add_outcome(rew, term.float())
+    assert buf.full
+    last = torch.from_numpy(rs.randn(N).astype(np.float32)).cuda()
+    buf.compute_returns_and_advantages(last, 0.99, 0.95)
+    adv, ret = O.gae(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), buf.dones.cpu().numpy(), last.cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(buf.advantages.cpu().numpy(), adv) and np.array_equal(buf.returns.cpu().numpy(), ret)
+    norm = O.normalize_advantages(adv)
+    from bbgpu import vec_env as VE
+    seen = 0
+    for boards, pieces, masks, actions, old_lp, a_n, r in buf.get_samples(500):
+        b = boards.shape[0]
+        assert boards.shape == (b, 8, 8) and pieces.shape == (b, 3, 8, 8) and masks.shape == (b, 192)
+        assert actions.dtype == torch.int64
+        seen += b
+    assert seen == T * N
+    # deterministic check of content: one batch of everything in storage order
+    mean, std = buf.advantage_mean_std()
+    got = ((buf.advantages.view(-1) - mean) / (std + 1e-8)).cpu().numpy()
+    np.testing.assert_allclose(got, norm, rtol=1e-4, atol=1e-5)
+    idx = torch.arange(T * N, device="cuda")
+    x, dense = buf._expand(idx)
+    x, dense = x.cpu().numpy(), dense.cpu().numpy()
+    for t in (0, T // 2, T - 1):
+        b, p, m = kept[t]
+        sl = slice(t * N, (t + 1) * N)
+        assert np.array_equal(x[sl, 0], VE.expand_board(b.view(np.uint64)))
+        assert np.array_equal(x[sl, 1:], VE.expand_pieces(p.view(np.uint32)))
+        assert np.array_equal(dense[sl], VE.expand_mask(m.view(np.uint64)).astype(np.float32))
+    # the reference-layout add() path stores the same content
+    buf2 = RolloutBuffer(2, N)
+    b, p, m = kept[0]
+    z = np.zeros(N, np.float32)
+    for _ in range(2):
+        buf2.add(VE.expand_board(b.view(np.uint64)), VE.expand_pieces(p.view(np.uint32)), VE.expand_mask(m.view(np.uint64)),
+                 np.zeros(N, np.int64), z, z, z, z)
+    x2, d2 = buf2._expand(torch.arange(N, device="cuda"))
+    assert np.array_equal(x2.cpu().numpy(), x[:N]) and np.array_equal(d2.cpu().numpy(), dense[:N])
+    venv.close()
+
+
+def test_ppo_update_metrics_match_independent_computation(torch):
+    """One epoch, one minibatch = the whole buffer, eval mode (no dropout / batch-stat noise):
+    the metrics of PPOAgent.update must equal ppo.py:372-406 evaluated with the oracle's
+    masked log-prob / entropy on the same logits."""
+    from bbgpu.ppo import PPOAgent, PPOConfig
+    from bbgpu.rollout import RolloutBuffer
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    from bbgpu import vec_env as VE
+    from oracle import bb_oracle as O
+    torch.manual_seed(0)
+    T, N = 8, 64
+    agent = PPOAgent(PPOConfig(num_epochs=1, batch_size=T * N, learning_rate=1e-3))
+    agent.eval()
+    venv = VectorizedBlockBlastEnv(N, seed=9, output="packed")
+    obs, _ = venv.reset()
+    buf = RolloutBuffer(T, N)
+    for t in range(T):
+        act, lp, val = agent.act(obs)
+        buf.add_obs(obs, act, lp, val)
+        obs, rew, term, _, _ = venv.step(act)
+        assert (rew > -5).all()                       # K3 only samples valid actions
+        buf.add_outcome(rew, term.float())
+    last = agent.values(obs)
+    # independent expectation, before the update changes the weights
+    idx = torch.arange(T * N, device="cuda")
+    x, dense = buf._expand(idx)
+    with torch.no_grad():
+        logits, values = agent.network.trunk(x)
+    adv, ret = O.gae(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), buf.dones.cpu().numpy(), last.cpu().numpy(), 0.99, 0.95)
+    a_n = O.normalize_advantages(adv)
+    acts = buf.actions.view(-1).cpu().numpy()
+    _, new_lp, ent = O.masked_policy_terms(logits.cpu().numpy(), dense.cpu().numpy(), acts)
+    old_lp = buf.log_probs.view(-1).cpu().numpy()
+    np.testing.assert_allclose(new_lp, old_lp, rtol=1e-4, atol=1e-5)     # K3's log-prob == oracle's on the same weights
+    ratio = np.exp(new_lp - old_lp)
+    pol = -np.minimum(ratio * a_n, np.clip(ratio, 0.8, 1.2) * a_n).mean()
+    vl = ((values.cpu().numpy() - ret.reshape(-1)) ** 2).mean()
+    before = [p.detach().clone() for p in agent.network.parameters()]
+    m = agent.update(buf, last)
+    assert abs(m["policy_loss"] - pol) < 1e-4 and abs(m["value_loss"] - vl) < 1e-3 * max(1.0, vl)
+    assert abs(m["entropy"] - ent.mean()) < 1e-4
+    assert abs(m["total_loss"] - (pol + 0.5 * vl - 0.01 * ent.mean())) < 1e-3 * max(1.0, vl)
+    assert m["clip_fraction"] < 1e-3 and abs(m["approx_kl"]) < 1e-4
+    assert any(not torch.equal(a, b) for a, b in zip(before, agent.network.parameters()))
+    venv.close()
+
+
+def test_short_training_run_and_checkpoint_keys(torch, tmp_path):
+    from bbgpu.train import train
+    from bbgpu.ppo import PPOAgent
+    cfg = {"training": {"num_envs": 256, "batch_size": 1024, "rollout_steps": 16, "total_timesteps": 3 * 256 * 16},
+           "ppo": {"num_epochs": 2}, "logging": {"log_interval": 1, "save_interval": 1},
+           "paths": {"checkpoint_dir": str(tmp_path / "ck"), "log_dir": str(tmp_path / "logs")}}
+    hist = train(cfg, seed=42)
+    assert len(hist) == 3 and hist[-1]["step"] == 3 * 256 * 16
+    assert 5 < hist[-1]["avg_length"] < 40 and hist[-1]["episodes"] > 50
+    assert np.isfinite([h["policy_loss"] for h in hist]).all() and hist[0]["entropy"] > 0.5
+    ck = torch.load(str(tmp_path / "ck" / "final.pt"), weights_only=False)
+    assert set(ck.keys()) == {"network_state_dict", "optimizer_state_dict", "config"}      # ppo.py:425-431
+    assert "conv_encoder.0.weight" in ck["network_state_dict"] and ck["config"]["num_epochs"] == 2
+    a = PPOAgent()
+    a.load(str(tmp_path / "ck" / "final.pt"))
+    assert os.path.exists(str(tmp_path / "ck" / "latest.pt")) and os.path.exists(str(tmp_path / "ck" / "checkpoint_%d.pt" % (3 * 256 * 16)))
+    # numpy-facing API of the agent on the reference-layout observation
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    v = VectorizedBlockBlastEnv(8, seed=1)
+    obs, _ = v.reset()
+    acts, lps, vals = a.select_actions(obs)
+    assert acts.shape == (8,) and lps.shape == (8,) and vals.shape == (8,)
+    assert all(obs["action_mask"][i, acts[i]] for i in range(8))
+    act1, info = a.select_action({k: obs[k][0] for k in ("board", "pieces", "action_mask")}, deterministic=True)
+    assert obs["action_mask"][0, act1] == 1 and set(info) == {"log_prob", "entropy", "value"}
+    assert a.get_values(obs).shape == (8,)
+    v.close()
