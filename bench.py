@@ -146,6 +146,100 @@ def cpu_c_port(n_threads, seconds, n_envs=4096):
     return done / (time.perf_counter() - t0), done
 
 
+def cpu_ppo_port(seconds_hint=20.0):
+    """PPO samples/s of the reference's schedule on the host CPU (config 1: 64 envs x 128 steps,
+    10 epochs x 4 minibatches of 2048), from TIMED COMPONENTS: the Python oracle env step, one
+    64-sample CNN forward and one 2048-sample forward+backward+Adam step of the same
+    5.29 M-parameter network in torch on the CPU.  A full iteration takes ~2 minutes on 8 cores
+    (BASELINE.md), so the components are timed and the schedule's total is computed."""
+    import numpy as np
+    import torch
+    from bbgpu.network import BlockBlastNetwork
+    from oracle import bb_oracle as O
+    torch.manual_seed(0)
+    net = BlockBlastNetwork()
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4, eps=1e-5)
+    envs = [O.Env(seed=100 + i, rng_factory=O.numpy_rng_factory) for i in range(64)]
+    vec = O.VecEnv(envs)
+    obs, _ = vec.reset()
+    rng = np.random.RandomState(0)
+    t0 = time.perf_counter()
+    n_env = 0
+    while time.perf_counter() - t0 < seconds_hint * 0.25:
+        obs, *_ = vec.step(vec.sample_valid_actions(rng))
+        n_env += 1
+    t_env = (time.perf_counter() - t0) / n_env
+    b, p = torch.from_numpy(obs["board"]), torch.from_numpy(obs["pieces"])
+    with torch.no_grad():
+        net.forward(b, p)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            net.forward(b, p)
+        t_fwd = (time.perf_counter() - t0) / 3
+    x = torch.rand(2048, 4, 8, 8).round()
+    m = torch.ones(2048, 192)
+    a = torch.zeros(2048, dtype=torch.long)
+    t_upd = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        _, lp, ent, v = net.evaluate_actions(x, m, a)
+        loss = -(lp.mean()) + 0.5 * (v ** 2).mean() - 0.01 * ent.mean()
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 0.5)
+        opt.step()
+        t_upd.append(time.perf_counter() - t0)
+    t_mb = min(t_upd)
+    iteration = 128 * (t_env + t_fwd) + 40 * t_mb
+    return 8192 / iteration, dict(env_vec_step_s=t_env, fwd64_s=t_fwd, minibatch2048_step_s=t_mb,
+                                  iteration_s=iteration, torch_threads=torch.get_num_threads())
+
+
+def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk):
+    """Masked-PPO collect + GAE + update on the device-resident path (BASELINE config 4 shape:
+    131,072 envs per GPU); returns samples/s and the phase times.  One warm-up iteration."""
+    import torch
+    import torch.distributed as dist
+    from bbgpu.ppo import PPOAgent, PPOConfig
+    from bbgpu.rollout import RolloutBuffer
+    from bbgpu.train import collect_rollout
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    agent = PPOAgent(PPOConfig(batch_size=minibatch, num_epochs=epochs, precision=precision), dev)
+    agent.train()
+    venv = VectorizedBlockBlastEnv(n_envs, seed=42, output="packed", global_env_offset=(64 + rank) * n_envs)
+    buf = RolloutBuffer(T, n_envs, device=dev)
+    obs, _ = venv.reset()
+    orig_act = agent.act
+    agent.act = lambda o, deterministic=False: orig_act(o, deterministic, chunk)
+    times = {}
+    for it in range(2):
+        ep = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(4)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        obs = collect_rollout(venv, agent, buf, obs, ep)
+        last = agent.values(obs, chunk)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        metrics = agent.update(buf, last)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t2 = time.perf_counter()
+        times = dict(collect_s=t1 - t0, update_s=t2 - t1, total_s=t2 - t0)
+    tt = torch.tensor([times["total_s"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    venv.close()
+    return dict(samples_per_sec=world * n_envs * T / float(tt.item()), envs_per_gpu=n_envs, rollout_steps=T,
+                minibatch=minibatch, epochs=epochs, precision=precision, act_chunk=chunk, **times,
+                entropy=metrics["entropy"], approx_kl=metrics["approx_kl"],
+                network="BlockBlastNetwork 5,290,113 params (PyTorch/cuDNN, not one of our kernels)",
+                grad_allreduce="1 flat NCCL all-reduce of 21.2 MB per optimiser step" if world > 1 else "n/a (1 GPU)")
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -186,6 +280,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU for the PPO leg (config 4: 1,048,576 / 8)")
+    ap.add_argument("--ppo-steps", type=int, default=8)
+    ap.add_argument("--ppo-minibatch", type=int, default=32768)
+    ap.add_argument("--ppo-epochs", type=int, default=2)
+    ap.add_argument("--ppo-precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +402,15 @@ def main():
     h2d = 4 * n
     d2h = 4 * n + (4 + 1 + 8 + 4 + 24 + 4 + 4) * n
 
+    ppo = None
+    if not args.no_ppo:
+        for e in envs:
+            e.close()
+        del outs
+        torch.cuda.empty_cache()
+        ppo = gpu_ppo_leg(rank, world, dev, args.ppo_envs, args.ppo_steps, args.ppo_minibatch, args.ppo_epochs,
+                          args.ppo_precision, 32768)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         per_launch_s = ms_max * 1e-3 / K
@@ -330,6 +439,8 @@ def main():
                       "episodes": s[1], "mean_episode_len": (s[3] / s[1]) if s[1] else None,
                       "mean_final_score": (s[2] / s[1]) if s[1] else None, "wall_s_timed_region": wall},
         }
+        if ppo is not None:
+            line["ppo"] = ppo
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             v_py, tot_py = cpu_python_port(1, args.cpu_seconds)
@@ -340,6 +451,11 @@ def main():
             line["cpu_baseline_c_port"] = {"value": v_c, "unit": UNIT, "cores": cores, "kind": "port",
                                            "sample": "%d env-steps: oracle/bb_oracle.c random-valid rollout, 4096 envs, "
                                                      "OpenMP over all host cores" % tot_c}
+            if ppo is not None:
+                v_ppo, parts = cpu_ppo_port(args.cpu_seconds)
+                line["ppo"]["cpu_baseline"] = {"value": v_ppo, "unit": "samples/s", "cores": parts["torch_threads"],
+                                               "kind": "port", "sample": "reference schedule (64 envs x 128 steps, 10 epochs x 4 x 2048) "
+                                               "computed from timed components", **parts}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -99,10 +99,21 @@ class PPOAgent:
 
     # ------------------------------------------------------------------ acting
     @torch.no_grad()
-    def act(self, obs, deterministic=False):
-        """Device fast path: returns (actions int32, log_probs, values) as CUDA tensors."""
+    def act(self, obs, deterministic=False, chunk=None):
+        """Device fast path: returns (actions int32, log_probs, values) as CUDA tensors.
+        ``chunk`` bounds the CNN batch (activation memory) for very large env counts; BatchNorm
+        in train mode then uses per-chunk statistics."""
         x, planes = self._obs_to_nchw(obs)
-        logits, value = self._trunk(x)
+        n = x.shape[0]
+        if chunk is None or n <= chunk:
+            logits, value = self._trunk(x)
+        else:
+            ls, vs = [], []
+            for s0 in range(0, n, chunk):
+                l, v = self._trunk(x[s0:s0 + chunk])
+                ls.append(l)
+                vs.append(v)
+            logits, value = torch.cat(ls), torch.cat(vs)
         act, logp, _ = self.network.head_from_logits(logits, planes, None, deterministic, need_entropy=False)
         return act, logp, value
 
@@ -122,9 +133,11 @@ class PPOAgent:
         return int(act.item()), {"log_prob": float(logp.item()), "entropy": float(ent.item()), "value": float(value.item())}
 
     @torch.no_grad()
-    def values(self, obs):
+    def values(self, obs, chunk=None):
         x, _ = self._obs_to_nchw({k: v for k, v in obs.items() if k != "action_mask"})
-        return self._trunk(x)[1]
+        if chunk is None or x.shape[0] <= chunk:
+            return self._trunk(x)[1]
+        return torch.cat([self._trunk(x[s0:s0 + chunk])[1] for s0 in range(0, x.shape[0], chunk)])
 
     def get_values(self, observations):
         """ppo.py:321-328."""

@@ -196,7 +196,7 @@ def test_short_training_run_and_checkpoint_keys(torch, tmp_path):
     assert "conv_encoder.0.weight" in ck["network_state_dict"] and ck["config"]["num_epochs"] == 2
     a = PPOAgent()
     a.load(str(tmp_path / "ck" / "final.pt"))
-    assert os.path.exists(str(tmp_path / "ck" / "latest.pt")) and os.path.exists(str(tmp_path / "ck" / "checkpoint_%d.pt" % (3 * 256 * 16)))
+    assert os.path.exists(str(tmp_path / "ck" / "latest.pt")) and os.path.exists(str(tmp_path / "ck" / ("checkpoint_%d.pt" % (3 * 256 * 16))))
     # numpy-facing API of the agent on the reference-layout observation
     from bbgpu.vec_env import VectorizedBlockBlastEnv
     v = VectorizedBlockBlastEnv(8, seed=1)
