@@ -60,8 +60,13 @@ class FlatGradBucket:
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = self._view(p, off)
             off += p.numel()
+
+    def _view(self, p, off):
+        # same sizes AND strides as the parameter (channels_last conv weights keep their
+        # layout, which is what autograd's gradient layout contract wants)
+        return self.flat[off:off + p.numel()].as_strided(p.size(), p.stride())
 
     def zero(self):
         self.flat.zero_()
@@ -70,8 +75,8 @@ class FlatGradBucket:
         """Re-attach the views if something replaced p.grad (e.g. zero_grad(set_to_none=True))."""
         off = 0
         for p in self.params:
-            if p.grad is None or p.grad.data_ptr() != self.flat[off:off + 1].data_ptr():
-                g = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != self.flat[off:off + 1].data_ptr() or p.grad.stride() != p.stride():
+                g = self._view(p, off)
                 if p.grad is not None:
                     g.copy_(p.grad)
                 p.grad = g
