@@ -37,6 +37,18 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -264,7 +276,7 @@ def run_reference_arm(args, rank, world):
                                        % (total, wall, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -291,6 +303,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner there)
+    # get stderr; the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -456,7 +475,7 @@ def main():
                 line["ppo"]["cpu_baseline"] = {"value": v_ppo, "unit": "samples/s", "cores": parts["torch_threads"],
                                                "kind": "port", "sample": "reference schedule (64 envs x 128 steps, 10 epochs x 4 x 2048) "
                                                "computed from timed components", **parts}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
