@@ -108,13 +108,14 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
         it.plan = __shfl_sync(FULL, item.plan, owner);
         const uint32_t tr = __shfl_sync(FULL, trio, owner);
         const uint32_t t = __shfl_sync(FULL, next, owner) + (uint32_t)(lane - g * ts);
-        const BBPiece p0 = bb_piece(T, tr & 0xFFu), p1 = bb_piece(T, (tr >> 8) & 0xFFu), p2 = bb_piece(T, (tr >> 16) & 0xFFu);
         BBBranch br;
-        br.bb = 0; br.m0 = 0; br.m1 = 0; br.sel = 0;
+        br.bb = 0; br.m0 = 0; br.m1 = 0; br.always = 0;
+        br.A.pm = br.A.inb = br.A.offs = 0; br.A.meta = 0;
+        br.B = br.A;
 #ifdef BB_PROFILE
         const long long q0 = BB_CLK();
 #endif
-        if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) br = bb_branch_open(it, p0, p1, p2, t);
+        if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) bb_branch_open(br, it, T, tr, t);
 #ifdef BB_PROFILE
         const long long q1 = BB_CLK();
         unsigned long long nunits = 0;
@@ -126,7 +127,7 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
             const bool work = in_team && !(found & team_mask) && ((br.m0 | br.m1) != 0ull);
             if (!__any_sync(FULL, work)) break;
             bool f = false;
-            if (work) f = bb_branch_unit(br, p0, p1, p2);
+            if (work) f = bb_branch_unit(br);
             found |= __ballot_sync(FULL, f);
 #ifdef BB_PROFILE
             nunits += 1;

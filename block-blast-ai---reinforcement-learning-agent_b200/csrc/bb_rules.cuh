@@ -135,18 +135,13 @@ BB_HD uint64_t bb_shr(uint64_t e, uint32_t o) {
 // repeats, so the first four steps need no predicate (31 of 37 pieces have <= 4 cells).
 BB_HD uint64_t bb_valid(uint64_t e, const BBPiece& p) {
     const uint32_t lo = (uint32_t)p.offs, hi = (uint32_t)(p.offs >> 32);
-    uint64_t v = p.inb;
-    v &= bb_shr(e, lo & 63u);
-    v &= bb_shr(e, (lo >> 6) & 63u);
-    v &= bb_shr(e, (lo >> 12) & 63u);
-    v &= bb_shr(e, (lo >> 18) & 63u);
+    uint64_t v = p.inb & bb_shr(e, lo & 63u) & bb_shr(e, (lo >> 6) & 63u);
+    v &= bb_shr(e, (lo >> 12) & 63u) & bb_shr(e, (lo >> 18) & 63u);
     const uint32_t n = BB_META_N(p.meta);
     if (n > 4) {
-        v &= bb_shr(e, (lo >> 24) & 63u);
-        v &= bb_shr(e, hi & 63u);
+        v &= bb_shr(e, (lo >> 24) & 63u) & bb_shr(e, hi & 63u);
         if (n > 6) {
-            v &= bb_shr(e, (hi >> 6) & 63u);
-            v &= bb_shr(e, (hi >> 12) & 63u);
+            v &= bb_shr(e, (hi >> 6) & 63u) & bb_shr(e, (hi >> 12) & 63u);
             v &= bb_shr(e, (hi >> 18) & 63u);
         }
     }
@@ -182,6 +177,20 @@ BB_HD bool bb_any_full(uint64_t b) {
 BB_HD uint64_t bb_clear_only(uint64_t b) {
     int l;
     return bb_clear(b, &l);
+}
+
+// b with its full rows/columns removed; *full tells whether there were any (one pass)
+BB_HD uint64_t bb_clear_if_full(uint64_t b, bool* full) {
+    uint64_t r = b & (b >> 4);
+    r &= r >> 2;
+    r &= r >> 1;
+    r &= BB_COL_A;
+    uint64_t c = b & (b >> 32);
+    c &= c >> 16;
+    c &= c >> 8;
+    c &= 0xFFull;
+    *full = (r | c) != 0ull;
+    return b & ~((r * 0xFFull) | (c * BB_COL_A));
 }
 
 // board.py:195-216: empty cells whose four neighbours are filled or off-board.
@@ -362,36 +371,40 @@ BB_HD int bb_classify(uint64_t b, const BBPiece& p0, const BBPiece& p1, const BB
 
 // A branch = one first-level placement already applied (board bb, cleared if it completed a
 // line) plus up to two second-level scans, processed one anchor ("unit") at a time:
-//   phase 0: piece f0 at each anchor of m0, then piece f1 must fit
-//   phase 1: piece f1 at each anchor of m1, then piece f0 must fit
+//   phase 0: piece A at each anchor of m0, then piece B must fit
+//   phase 1: piece B at each anchor of m1, then piece A must fit
 // A phase in "always" mode tests the leaf for every anchor; otherwise only for anchors whose
 // placement completes a line (the no-clear case is covered elsewhere: fact P).
 struct BBBranch {
     uint64_t bb, m0, m1;
-    uint32_t sel;      // bits 0-1 f0, bits 2-3 f1, bit 4 phase-0 always, bit 5 phase-1 always
+    BBPiece A, B;
+    uint32_t always;   // bit 0: phase 0 always, bit 1: phase 1 always
 };
 
 BB_HD bool bb_can_complete_line(const BBLines& L, const BBPiece& p) {
     return bb_row_within(L, (int)BB_META_MAXROW(p.meta)) || bb_col_within(L, (int)BB_META_MAXCOL(p.meta));
 }
 
-// open branch t of a HARD item, t in [0, nA + nB)
-BB_HD BBBranch bb_branch_open(const BBItem& it, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2, uint32_t t) {
+#define BB_TRIO_ID(trio, i) (((trio) >> (8 * (i))) & 0xFFu)
+
+// open branch t of a HARD item, t in [0, nA + nB); pieces are fetched by role from the table
+BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uint32_t trio, uint32_t t) {
     BB_WORK(branches, 1);
-    BBBranch br;
     const uint32_t nA = BB_PLAN_NA(it.plan);
     if (t < nA) {
         const int x = (int)(it.plan & 3u), y = (int)((it.plan >> 2) & 3u), z = (int)((it.plan >> 4) & 3u);
         const uint64_t vx = x == 0 ? it.v[0] : (x == 1 ? it.v[1] : it.v[2]);
-        const BBPiece px = bb_pick3(p0, p1, p2, x);
-        const uint64_t b1 = it.b | (px.pm << bb_select(vx, (int)t));
-        br.bb = bb_any_full(b1) ? bb_clear_only(b1) : b1;
+        const uint64_t pmx = T->mask[BB_TRIO_ID(trio, x)];
+        bool full;
+        br.bb = bb_clear_if_full(it.b | (pmx << bb_select(vx, (int)t)), &full);
+        br.A = bb_piece(T, BB_TRIO_ID(trio, y));
+        br.B = bb_piece(T, BB_TRIO_ID(trio, z));
         BB_WORK(valid_calls, 2);
         // z must still fit beside x at all, else no packing goes through this anchor
-        br.m0 = bb_valid(~br.bb, bb_pick3(p0, p1, p2, z)) ? bb_valid(~br.bb, bb_pick3(p0, p1, p2, y)) : 0ull;
+        br.m0 = bb_valid(~br.bb, br.B) ? bb_valid(~br.bb, br.A) : 0ull;
         br.m1 = 0ull;
-        br.sel = (uint32_t)y | ((uint32_t)z << 2) | 16u;
-        return br;
+        br.always = 1u;
+        return;
     }
     int k = (int)(t - nA);
     int i = 0;
@@ -399,44 +412,47 @@ BB_HD BBBranch bb_branch_open(const BBItem& it, const BBPiece& p0, const BBPiece
     if (k >= n0) { k -= n0; i = 1; if (k >= n1) { k -= n1; i = 2; } }
     const int j = i == 0 ? 1 : 0, l = i == 2 ? 1 : 2;
     const uint64_t vi = i == 0 ? it.v[0] : (i == 1 ? it.v[1] : it.v[2]);
-    const BBPiece pi = bb_pick3(p0, p1, p2, i);
-    const uint64_t b1 = it.b | (pi.pm << bb_select(vi, k));
-    const bool full1 = bb_any_full(b1);
-    br.bb = full1 ? bb_clear_only(b1) : b1;
-    const BBPiece pj = bb_pick3(p0, p1, p2, j), pl = bb_pick3(p0, p1, p2, l);
+    const uint64_t pmi = T->mask[BB_TRIO_ID(trio, i)];
+    bool full1;
+    br.bb = bb_clear_if_full(it.b | (pmi << bb_select(vi, k)), &full1);
+    br.A = bb_piece(T, BB_TRIO_ID(trio, j));
+    br.B = bb_piece(T, BB_TRIO_ID(trio, l));
     const BBLines L = bb_lines(br.bb);
     BB_WORK(valid_calls, 2);
-    // first placement cleared a line: everything about (j,l) is open; j first covers the
-    // packings of both orders, l first matters only when l itself clears.  Nothing cleared:
-    // a packing of (j,l) beside i is stage A's business, only clearing placements matter.
-    br.m0 = (full1 || bb_can_complete_line(L, pj)) ? bb_valid(~br.bb, pj) : 0ull;
-    br.m1 = bb_can_complete_line(L, pl) ? bb_valid(~br.bb, pl) : 0ull;
-    br.sel = (uint32_t)j | ((uint32_t)l << 2) | (full1 ? 16u : 0u);
-    return br;
+    // first placement cleared a line: everything about (A,B) is open; A first covers the
+    // packings of both orders, B first matters only when B itself clears.  Nothing cleared:
+    // a packing of (A,B) beside i is stage A's business, only clearing placements matter.
+    br.m0 = (full1 || bb_can_complete_line(L, br.A)) ? bb_valid(~br.bb, br.A) : 0ull;
+    br.m1 = bb_can_complete_line(L, br.B) ? bb_valid(~br.bb, br.B) : 0ull;
+    br.always = full1 ? 1u : 0u;
 }
 
 // process one unit of an open branch (precondition: (m0 | m1) != 0); true = trio solvable
-BB_HD bool bb_branch_unit(BBBranch& br, const BBPiece& p0, const BBPiece& p1, const BBPiece& p2) {
+BB_HD bool bb_branch_unit(BBBranch& br) {
     const bool ph = br.m0 == 0ull;
     uint64_t m = ph ? br.m1 : br.m0;
     const int a = bb_ctz(m);
     m &= m - 1;
     if (ph) br.m1 = m; else br.m0 = m;
-    const int fi = (int)((br.sel >> (ph ? 2 : 0)) & 3u), si = (int)((br.sel >> (ph ? 0 : 2)) & 3u);
-    const uint64_t pm = fi == 0 ? p0.pm : (fi == 1 ? p1.pm : p2.pm);
-    const uint64_t b2 = br.bb | (pm << a);
-    const bool full = bb_any_full(b2);
+    bool full;
+    const uint64_t b2 = bb_clear_if_full(br.bb | ((ph ? br.B.pm : br.A.pm) << a), &full);
     BB_WORK(clear_iters, 1);
-    if (!full && !((br.sel >> (ph ? 5 : 4)) & 1u)) return false;
+    if (!full && !((br.always >> (ph ? 1 : 0)) & 1u)) return false;
     BB_WORK(valid_calls, 1);
-    return bb_valid(~(full ? bb_clear_only(b2) : b2), bb_pick3(p0, p1, p2, si)) != 0ull;
+    BBPiece s2;
+    s2.pm = 0;
+    s2.inb = ph ? br.A.inb : br.B.inb;
+    s2.offs = ph ? br.A.offs : br.B.offs;
+    s2.meta = ph ? br.A.meta : br.B.meta;
+    return bb_valid(~b2, s2) != 0ull;
 }
 
 // sequential drivers (host build): same branches and units, in index order
-BB_HD bool bb_branch(const BBItem& it, const BBPiece P[3], uint32_t t) {
-    BBBranch br = bb_branch_open(it, P[0], P[1], P[2], t);
+BB_HD bool bb_branch(const BBItem& it, const BBTables* T, uint32_t trio, uint32_t t) {
+    BBBranch br;
+    bb_branch_open(br, it, T, trio, t);
     while (br.m0 | br.m1)
-        if (bb_branch_unit(br, P[0], P[1], P[2])) return true;
+        if (bb_branch_unit(br)) return true;
     return false;
 }
 
@@ -452,7 +468,7 @@ BB_HD bool bb_solvable(uint64_t b, const BBTables* T, uint32_t trio) {
     BB_WORK(slow, 1);
     const uint32_t n = BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan);
     for (uint32_t t = 0; t < n; ++t)
-        if (bb_branch(it, P, t)) return true;
+        if (bb_branch(it, T, trio, t)) return true;
     return false;
 }
 

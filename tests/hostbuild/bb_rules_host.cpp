@@ -100,7 +100,7 @@ int bbh_item_branch(uint64_t board, int p0, int p1, int p2, uint32_t t) {
     BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
     BBItem it;
     bb_classify(board, P[0], P[1], P[2], &it);
-    return bb_branch(it, P, t) ? 1 : 0;
+    return bb_branch(it, &g_tables, (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16), t) ? 1 : 0;
 }
 void bbh_work_reset() { memset(&g_bb_work, 0, sizeof(g_bb_work)); }
 
