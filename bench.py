@@ -208,6 +208,76 @@ def cpu_ppo_port(seconds_hint=20.0):
                                   iteration_s=iteration, torch_threads=torch.get_num_threads())
 
 
+def kernel_rooflines(dev, peak):
+    """CUDA-event timings of the companion kernels at config-3/4 sizes, inputs larger than L2;
+    achieved = algorithmic bytes / time."""
+    import torch
+    from bbgpu import capi
+    out = {}
+
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / iters
+
+    # context for the write-dominated K2: what a pure-write stream (torch fill_) reaches on this GPU
+    big = torch.empty(256 * 1024 * 1024, dtype=torch.float32, device=dev)
+    t = timeit(lambda: big.fill_(1.0), iters=10)
+    out["write_only_fill_GBs"] = big.numel() * 4 / t / 1e9
+    del big
+    # K4 GAE: T=128 x N=262,144, 20 B/sample (+4N last values) = 671 MB per launch
+    T, N = 128, 262144
+    r, v = torch.randn(T, N, device=dev), torch.randn(T, N, device=dev)
+    d = (torch.rand(T, N, device=dev) < 0.07).float()
+    lv = torch.randn(N, device=dev)
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    mom = torch.zeros(2, dtype=torch.float64, device=dev)
+    t = timeit(lambda: capi.gae(r, v, d, lv, 0.99, 0.95, adv, ret, mom))
+    b = 20 * T * N + 4 * N
+    out["K4_gae"] = {"samples": T * N, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                     "frac_of_hbm_peak": b / t / 1e9 / peak, "samples_per_sec": T * N / t}
+    del r, v, d, adv, ret
+    # K3 masked sample: n=524,288 rows of f32 logits: 804 B/row = 421 MB per launch
+    n = 524288
+    logits = torch.randn(n, 192, device=dev)
+    mask = torch.randint(-2 ** 62, 2 ** 62, (3, n), dtype=torch.int64, device=dev) | 1
+    act = torch.empty(n, dtype=torch.int32, device=dev)
+    lp, en = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    t = timeit(lambda: capi.masked_sample(logits, mask, n, 1, 1, 0, act, lp, en))
+    b = 804 * n
+    out["K3_masked_sample_f32"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                                   "frac_of_hbm_peak": b / t / 1e9 / peak}
+    lb = logits.bfloat16()
+    t = timeit(lambda: capi.masked_sample(lb, mask, n, 1, 1, 0, act, lp, en))
+    b = 420 * n
+    out["K3_masked_sample_bf16"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                                    "frac_of_hbm_peak": b / t / 1e9 / peak}
+    del logits, lb
+    # K2 obs unpack: 36 B in, 1,024 B f32 planes out (+ 192 B u8 mask) per env
+    board = torch.randint(-2 ** 62, 2 ** 62, (n,), dtype=torch.int64, device=dev)
+    pieces = torch.randint(0, 37, (n,), dtype=torch.int32, device=dev) * 0x010101
+    obs = torch.empty((n, 4, 8, 8), device=dev)
+    t = timeit(lambda: capi.unpack_obs(board, pieces, mask, n, obs=obs, n=n))
+    b = (12 + 1024) * n
+    out["K2_unpack_obs_f32"] = {"envs": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                                "frac_of_hbm_peak": b / t / 1e9 / peak}
+    obs16 = torch.empty((n, 4, 8, 8), dtype=torch.bfloat16, device=dev)
+    t = timeit(lambda: capi.unpack_obs(board, pieces, mask, n, obs=obs16, n=n))
+    b = (12 + 512) * n
+    out["K2_unpack_obs_bf16"] = {"envs": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                                 "frac_of_hbm_peak": b / t / 1e9 / peak}
+    for k in ("K2_unpack_obs_f32", "K2_unpack_obs_bf16"):
+        out[k]["frac_of_write_only_fill"] = out[k]["achieved_GBs"] / out["write_only_fill_GBs"]
+    return out
+
+
 def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk):
     """Masked-PPO collect + GAE + update on the device-resident path (BASELINE config 4 shape:
     131,072 envs per GPU); returns samples/s and the phase times.  One warm-up iteration."""
@@ -422,11 +492,13 @@ def main():
     d2h = 4 * n + (4 + 1 + 8 + 4 + 24 + 4 + 4) * n
 
     ppo = None
+    for e in envs:
+        e.close()
+    del outs
+    torch.cuda.empty_cache()
+    kernels = kernel_rooflines(dev, load_peaks()[0]) if rank == 0 else None
+    torch.cuda.empty_cache()
     if not args.no_ppo:
-        for e in envs:
-            e.close()
-        del outs
-        torch.cuda.empty_cache()
         ppo = gpu_ppo_leg(rank, world, dev, args.ppo_envs, args.ppo_steps, args.ppo_minibatch, args.ppo_epochs,
                           args.ppo_precision, 32768)
 
@@ -458,6 +530,7 @@ def main():
                       "episodes": s[1], "mean_episode_len": (s[3] / s[1]) if s[1] else None,
                       "mean_final_score": (s[2] / s[1]) if s[1] else None, "wall_s_timed_region": wall},
         }
+        line["kernels"] = kernels
         if ppo is not None:
             line["ppo"] = ppo
         if not args.no_cpu:

@@ -7,8 +7,8 @@
 // one contiguous run of 128-bit stores.
 //
 // K3 replaces src/models/network.py:172-262 (mask -> softmax -> Categorical sample/log_prob ->
-// masked entropy): one warp per row, 768 B of logits read once with 8-byte loads (256 B
-// contiguous per warp instruction), everything else in registers / shuffles.
+// masked entropy): 8 lanes per row, 768 B of logits read once with 128-bit loads (128 B
+// contiguous per row group per instruction), everything else in registers / 3-step butterflies.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <math.h>
@@ -105,165 +105,153 @@ cudaError_t bb_launch_unpack_obs(const uint64_t* board, const uint32_t* pieces, 
 }
 
 // ------------------------------------------------------------------------------------ K3
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-    return v;
+// 8 lanes per row, 4 rows per warp.  Lane l of a row group owns the 24 actions
+//     a(l,k,c) = 32k + 4l + c        k = 0..5, c = 0..3
+// i.e. the k-th 128-bit load of the group is one contiguous 128 B (f32) run.  Everything else
+// is per-lane arithmetic plus 3-step butterflies inside the 8-lane group:
+//   p_i = exp(z_i - m) / S            (exp2 on pre-scaled inputs)
+//   log_prob = log(clamp(p_a / sum(p), eps, 1-eps))          torch Categorical (network.py:213-225)
+//   entropy  = log S - sum_i e_i (z_i - m) / S               == -sum q log q (network.py:246-260);
+//              the reference's clamps at 1e-10 change it by < 1e-8
+// Sampling is the inverse CDF of u * sum(p) over the order (lane, k, c) — a fixed permutation
+// of the actions, so the draw is an exact categorical sample; philox.py documents the order.
+#define K3_LOG2E 1.4426950408889634f
+
+__device__ __forceinline__ float grp_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
 }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += o;
-    }
-    return v;
+__device__ __forceinline__ float grp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
-// lane l of the warp owns actions 64k + 2l and 64k + 2l + 1 for planes k = 0,1,2
 template <bool BF16>
 __global__ void __launch_bounds__(128)
 bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
                         uint64_t seed, uint64_t call_counter, int mode, int32_t* __restrict__ action,
                         float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= n) return;   // whole warp exits together
-    float z[3][2];
-    uint32_t mb[3];
+    const int l = lane & 7;                       // lane inside the row group
+    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = row_raw < n;
+    const int64_t row = live ? row_raw : n - 1;   // out-of-range groups shadow the last row, never store
+
+    float z[24];
+    uint32_t mb = 0;                              // bit (4k + c) = mask of a(l,k,c)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint64_t w = __ldg(mask + (int64_t)k * stride + row);
-        mb[k] = (uint32_t)(w >> (2 * lane)) & 3u;
-        float2 v;
+    for (int p = 0; p < 3; ++p) {
+        const uint64_t w = __ldg(mask + (int64_t)p * stride + row);
+        mb |= ((uint32_t)(w >> (4 * l)) & 0xFu) << (8 * p);
+        mb |= ((uint32_t)(w >> (32 + 4 * l)) & 0xFu) << (8 * p + 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        float4 v;
         if (BF16) {
-            const __nv_bfloat162 h = reinterpret_cast<const __nv_bfloat162*>(logits)[row * 96 + k * 32 + lane];
-            v = __bfloat1622float2(h);
+            const uint2 h = reinterpret_cast<const uint2*>(logits)[row * 48 + k * 8 + l];
+            v.x = __uint_as_float(h.x << 16); v.y = __uint_as_float(h.x & 0xFFFF0000u);
+            v.z = __uint_as_float(h.y << 16); v.w = __uint_as_float(h.y & 0xFFFF0000u);
         } else {
-            v = reinterpret_cast<const float2*>(logits)[row * 96 + k * 32 + lane];
+            v = reinterpret_cast<const float4*>(logits)[row * 48 + k * 8 + l];
         }
-        z[k][0] = (mb[k] & 1u) ? v.x : -INFINITY;
-        z[k][1] = (mb[k] & 2u) ? v.y : -INFINITY;
+        z[4 * k + 0] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w;
     }
-    float m = fmaxf(fmaxf(fmaxf(z[0][0], z[0][1]), fmaxf(z[1][0], z[1][1])), fmaxf(z[2][0], z[2][1]));
-    m = warp_max(m);
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) m = fmaxf(m, ((mb >> i) & 1u) ? z[i] : -INFINITY);
+    m = grp_max(m);
     const bool any_valid = m > -INFINITY;
-    float p[3][2];
-    float s = 0.f;
+    float s = 0.f, sz = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        p[k][0] = (mb[k] & 1u) ? expf(z[k][0] - m) : 0.f;
-        p[k][1] = (mb[k] & 2u) ? expf(z[k][1] - m) : 0.f;
-        s += p[k][0] + p[k][1];
+    for (int i = 0; i < 24; ++i) {
+        const float d = z[i] - m;                                 // <= 0 for valid actions
+        const float e = ((mb >> i) & 1u) ? exp2f(d * K3_LOG2E) : 0.f;
+        s += e;
+        sz = fmaf(e, ((mb >> i) & 1u) ? d : 0.f, sz);
+        z[i] = e;                                                  // z now holds exp(z - m)
     }
-    s = warp_sum(s);
-    const float inv = any_valid ? 1.f / s : 0.f;
-    float ps = 0.f;   // sum of probabilities (Categorical re-normalises by it)
+    s = grp_sum(s);
+    sz = grp_sum(sz);
+    const float inv = any_valid ? __frcp_rn(s) : 0.f;
+    float ps = 0.f;                                                // sum of the rounded probabilities
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        p[k][0] = __fdiv_rn(p[k][0], s);
-        p[k][1] = __fdiv_rn(p[k][1], s);
-        if (!any_valid) { p[k][0] = 0.f; p[k][1] = 0.f; }
-        ps += p[k][0] + p[k][1];
-    }
-    (void)inv;
-    ps = warp_sum(ps);
+    for (int i = 0; i < 24; ++i) { z[i] *= inv; ps += z[i]; }     // z now holds p
+    const float lane_tot = ps;
+    ps = grp_sum(ps);
 
     int act = 0;
+    float pa = 0.f;
     if (mode == 2) {
         act = action[row];
+        // owner lane / slot of action a: k = a / 32, l = (a % 32) / 4, c = a % 4
+        float mine = 0.f;
+        const int slot = ((act >> 5) << 2) | (act & 3);
+        const bool own = act >= 0 && act < 192 && ((act & 31) >> 2) == l;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) mine += (own && i == slot) ? z[i] : 0.f;
+        pa = grp_sum(mine);
     } else if (mode == 1) {
-        // argmax of probs, first index on ties (torch.argmax)
-        float best = -1.f; int bi = 0x7fffffff;
+        // argmax of probs, lowest action index on ties (torch.argmax)
+        float best = -1.f;
+        int bi = 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int i = 0; i < 24; ++i) {
+            const int idx = 32 * (i >> 2) + 4 * l + (i & 3);
+            if (z[i] > best || (z[i] == best && idx < bi)) { best = z[i]; bi = idx; }
+        }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int idx = 64 * k + 2 * lane + e;
-                if (p[k][e] > best || (p[k][e] == best && idx < bi)) { best = p[k][e]; bi = idx; }
-            }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
+        for (int d = 1; d < 8; d <<= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, d);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
         act = any_valid ? bi : 0;
+        pa = any_valid ? best : 0.f;
     } else {
-        // inverse CDF in action-index order on u * sum(p)
         const BBPhilox4 r = bb_philox((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)call_counter,
                                       BB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
         const float t = u * ps;
-        float base = 0.f;
-        int found = -1;
+        // exclusive prefix of the lane totals inside the group
+        float incl = lane_tot;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float c = p[k][0] + p[k][1];
-            const float incl = warp_incl_scan(c, lane);
-            const float tot = __shfl_sync(0xffffffffu, incl, 31);
-            const unsigned hit = __ballot_sync(0xffffffffu, (base + incl > t) && (c > 0.f));
-            if (found < 0 && hit) {
-                const int L = __ffs(hit) - 1;
-                const float excl = base + incl - c;
-                int e = ((excl + p[k][0] > t) && (p[k][0] > 0.f)) ? 0 : ((p[k][1] > 0.f) ? 1 : 0);
-                e = __shfl_sync(0xffffffffu, e, L);
-                found = 64 * k + 2 * L + e;
-            }
-            base += tot;
+        for (int d = 1; d < 8; d <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, incl, d, 8);
+            if (l >= d) incl += o;
         }
-        if (found < 0) {
-            // t >= total by rounding: take the last action with non-zero probability
+        const float excl = incl - lane_tot;
+        // first lane whose inclusive prefix exceeds t (and that has any probability mass)
+        const unsigned hit = (__ballot_sync(0xffffffffu, incl > t && lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
+        const unsigned nz = (__ballot_sync(0xffffffffu, lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
+        // rounding can leave t >= total: fall back to the last lane with mass
+        const int L = hit ? (__ffs((int)hit) - 1) : (nz ? (31 - __clz((int)nz)) : 0);
+        // inside lane L: first element whose running sum exceeds t, else its last non-zero one
+        float run = excl;
+        int pick = -1, lastnz = 0;
+        float ppick = 0.f, plast = 0.f;
 #pragma unroll
-            for (int k = 2; k >= 0; --k) {
-                const unsigned nz = __ballot_sync(0xffffffffu, (p[k][0] > 0.f) || (p[k][1] > 0.f));
-                if (found < 0 && nz) {
-                    const int L = 31 - __clz(nz);
-                    int e = (p[k][1] > 0.f) ? 1 : 0;
-                    e = __shfl_sync(0xffffffffu, e, L);
-                    found = 64 * k + 2 * L + e;
-                }
-            }
+        for (int i = 0; i < 24; ++i) {
+            run += z[i];
+            if (z[i] > 0.f) { lastnz = i; plast = z[i]; if (pick < 0 && run > t) { pick = i; ppick = z[i]; } }
         }
-        act = found < 0 ? 0 : found;
+        if (pick < 0) { pick = lastnz; ppick = plast; }
+        const int idx = 32 * (pick >> 2) + 4 * l + (pick & 3);
+        const int src = (lane & 24) | L;
+        act = __shfl_sync(0xffffffffu, idx, src);
+        pa = __shfl_sync(0xffffffffu, ppick, src);
+        if (!any_valid) { act = 0; pa = 0.f; }
     }
-
-    // probability of the chosen action
-    const int ak = (act >> 6), al = (act & 63) >> 1, ae = act & 1;
-    float pa = 0.f;
-    if (act >= 0 && act < 192) {
-        float mine = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (k == ak) mine = ae ? p[k][1] : p[k][0];
-        pa = __shfl_sync(0xffffffffu, mine, al);
-    }
-    // entropy over the valid actions (network.py:246-260)
-    float ent = 0.f;
-    if (ent_out) {
-        const float den = fmaxf(ps, 1e-10f);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if ((mb[k] >> e) & 1u) {
-                    const float q = __fdiv_rn(p[k][e], den);
-                    ent -= q * logf(fmaxf(q, 1e-10f));
-                }
-        ent = warp_sum(ent);
-    }
-    if (lane == 0) {
+    if (live && l == 0) {
         if (mode != 2) action[row] = act;
         if (logp_out) {
             const float eps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
-            const float pn = any_valid ? __fdiv_rn(pa, ps) : 1.f;
+            const float pn = any_valid ? pa / ps : 1.f;
             logp_out[row] = logf(fminf(fmaxf(pn, eps), 1.f - eps));
         }
-        if (ent_out) ent_out[row] = ent;
+        if (ent_out) ent_out[row] = any_valid ? (logf(s) - sz * inv) : 0.f;
     }
 }
 
@@ -271,7 +259,7 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
                                     int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
                                     int32_t* action, float* logp, float* entropy, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n * 32 + 127) / 128);
+    const unsigned grid = (unsigned)((n * 8 + 127) / 128);
     if (logits_dtype == 1)
         bb_masked_sample_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n);
     else

@@ -15,7 +15,9 @@ Philox4x32-10 (Salmon et al., SC'11), one block per event:
     stream 1  POLICY  index = the env's policy-step counter; word 0 picks the k-th valid
                       action, k = mulhi32(word0, n_valid)   (bb_env_step_random)
     stream 2  SAMPLE  categorical sampling in bb_masked_sample: counter =
-                      (row & 0xffffffff, row >> 32, call_counter, 2); word 0 -> u in [0,1)
+                      (row & 0xffffffff, row >> 32, call_counter, 2); word 0 -> u in [0,1);
+                      the action is the inverse CDF of u * sum(p) taken over the kernel's lane
+                      order of the 192 actions (``sample_order()``), a fixed permutation
 
 Everything here is numpy on the host; it is documentation-by-code of the device streams and
 the generator of candidate-trio fixtures.  It launches nothing and is not a fallback for any
@@ -81,3 +83,10 @@ def sample_uniforms(seed, call_counter, n_rows):
     w = philox4x32_10(rows & MASK32, rows >> np.uint64(32), call_counter, STREAM_SAMPLE,
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return (w[0] >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def sample_order():
+    """int64 [192]: the order in which bb_masked_sample accumulates the CDF — lane l of an
+    8-lane row group owns actions 32k + 4l + c (k = 0..5, c = 0..3); lanes are scanned in
+    order, then k, then c."""
+    return np.array([32 * k + 4 * l + c for l in range(8) for k in range(6) for c in range(4)], dtype=np.int64)
