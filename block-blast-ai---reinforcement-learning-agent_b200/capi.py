@@ -58,6 +58,7 @@ def lib():
     L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.bb_env_observe.argtypes = [vp, vp, vp, vp, vp]
+    L.bb_env_sample_valid_actions.argtypes = [vp, u64, vp, vp, vp]
     L.bb_env_get_state.argtypes = [vp, vp, vp]
     L.bb_env_set_state.argtypes = [vp, vp, vp]
     L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -140,6 +141,10 @@ class EnvHandle:
     def step_random(self, n_steps=1, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
         check(lib().bb_env_step_random(self.h, int(n_steps), ptr(actions_out), ptr(rewards), ptr(terminated),
                                        ptr(mask_out), ptr(stats), current_stream()))
+
+    def sample_valid_actions(self, call_counter, actions_out=None, h_actions_out=None):
+        check(lib().bb_env_sample_valid_actions(self.h, int(call_counter), ptr(actions_out), ptr(h_actions_out),
+                                                current_stream()))
 
     def observe(self, board_out=None, pieces_out=None, mask_out=None):
         check(lib().bb_env_observe(self.h, ptr(board_out), ptr(pieces_out), ptr(mask_out), current_stream()))

@@ -36,6 +36,8 @@ static const double BB_DEFAULT_CFG[7] = {1.0, 0.01, -1.0, -0.05, 0.02, 0.5, 0.00
 
 extern "C" {
 
+static int ensure_staging(bb_env* e);
+
 int bb_version(void) { return BB_ABI_VERSION; }
 const char* bb_last_error(void) { return g_err; }
 
@@ -125,6 +127,23 @@ int bb_env_step_random(bb_env* e, int32_t n_steps, int32_t* actions_out, float* 
 int bb_env_observe(bb_env* e, uint64_t* board_out, uint32_t* pieces_out, uint64_t* mask_out, void* stream) {
     if (!e) return fail(-1, "bb_env_observe: env is NULL");
     BB_CUDA(bb_launch_observe(e->arr, board_out, pieces_out, mask_out, (cudaStream_t)stream), "bb_env_observe launch");
+    return 0;
+}
+
+int bb_env_sample_valid_actions(bb_env* e, uint64_t call_counter, int32_t* actions_out, int32_t* h_actions_out, void* stream) {
+    if (!e) return fail(-1, "bb_env_sample_valid_actions: env is NULL");
+    if (!actions_out && !h_actions_out) return fail(-1, "bb_env_sample_valid_actions: no output given");
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t* d = actions_out;
+    if (!d) {
+        if (int rc = ensure_staging(e)) return rc;
+        d = e->d_actions;
+    }
+    BB_CUDA(bb_launch_sample_valid(e->arr, call_counter, d, s), "bb_env_sample_valid_actions launch");
+    if (h_actions_out) {
+        BB_CUDA(cudaMemcpyAsync(h_actions_out, d, e->arr.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H actions");
+        BB_CUDA(cudaStreamSynchronize(s), "bb_env_sample_valid_actions sync");
+    }
     return 0;
 }
 

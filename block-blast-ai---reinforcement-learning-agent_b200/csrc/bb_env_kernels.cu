@@ -385,6 +385,26 @@ bb_observe_kernel(BBEnvArrays E, uint64_t* __restrict__ board_out, uint32_t* __r
     }
 }
 
+// uniform random valid action of the current state (sample_valid_actions, wrappers.py:133-136):
+// k-th set bit of the 192-bit mask, k = mulhi(word, n_valid); 0 when nothing is valid.  Uses
+// Philox stream 3 with a caller-supplied call counter; the env state is not modified.
+#define BB_STREAM_SAMPLE_VALID 3u
+__global__ void __launch_bounds__(BB_STEP_THREADS)
+bb_sample_valid_kernel(BBEnvArrays E, uint64_t call_counter, int32_t* __restrict__ actions_out) {
+    __shared__ BBTables T;
+    bb_stage_tables(&T);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    BBState s;
+    bb_load_state(E, i, s);
+    uint64_t m[3];
+    bb_action_mask(s, &T, m);
+    const uint64_t env_id = (uint64_t)(E.env_offset + i);
+    const BBPhilox4 r = bb_philox((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)call_counter,
+                                  BB_STREAM_SAMPLE_VALID, (uint32_t)E.seed, (uint32_t)(E.seed >> 32));
+    actions_out[i] = bb_pick_action(m, r.x);
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -414,5 +434,10 @@ cudaError_t bb_launch_reset(const BBEnvArrays& E, const uint8_t* reset_mask, uin
 cudaError_t bb_launch_observe(const BBEnvArrays& E, uint64_t* board_out, uint32_t* pieces_out,
                               uint64_t* mask_out, cudaStream_t stream) {
     bb_observe_kernel<<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(E, board_out, pieces_out, mask_out);
+    return cudaGetLastError();
+}
+
+cudaError_t bb_launch_sample_valid(const BBEnvArrays& E, uint64_t call_counter, int32_t* actions_out, cudaStream_t stream) {
+    bb_sample_valid_kernel<<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(E, call_counter, actions_out);
     return cudaGetLastError();
 }

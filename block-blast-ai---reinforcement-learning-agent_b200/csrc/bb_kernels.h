@@ -29,6 +29,7 @@ cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, 
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
                                   uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream);
 cudaError_t bb_launch_reset(const BBEnvArrays& E, const uint8_t* reset_mask, uint64_t* mask_out, cudaStream_t stream);
+cudaError_t bb_launch_sample_valid(const BBEnvArrays& E, uint64_t call_counter, int32_t* actions_out, cudaStream_t stream);
 cudaError_t bb_launch_observe(const BBEnvArrays& E, uint64_t* board_out, uint32_t* pieces_out,
                               uint64_t* mask_out, cudaStream_t stream);
 

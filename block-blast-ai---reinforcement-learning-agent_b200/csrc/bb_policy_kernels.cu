@@ -17,41 +17,58 @@
 __constant__ uint64_t c_piece_cells[BB_NUM_PIECES + 3] = BB_PIECE_MASKS;
 
 // ------------------------------------------------------------------------------------ K2
+// One item = 16 output bytes, so consecutive lanes always store consecutive 16-byte pieces
+// (full 32-byte sectors per instruction): bf16 item = (env, channel, row) -> 8 values,
+// f32 item = (env, channel, row, half) -> 4 values.
 template <bool BF16>
-__global__ void __launch_bounds__(256)
-bb_unpack_obs_kernel(const uint64_t* __restrict__ board, const uint32_t* __restrict__ pieces,
-                     void* __restrict__ obs, int64_t n) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (env, channel, row)
-    const int64_t env = t >> 5;
-    if (env >= n) return;
-    const int ch = (int)(t >> 3) & 3, row = (int)t & 7;
-    uint64_t plane;
-    if (ch == 0) {
-        plane = __ldg(board + env);
-    } else {
-        const uint32_t pw = __ldg(pieces + env);
-        const uint32_t id = (pw >> (8 * (ch - 1))) & 0xFFu;
-        const bool used = (pw >> (24 + ch - 1)) & 1u;
-        plane = used ? 0ull : c_piece_cells[id < BB_NUM_PIECES ? id : BB_NUM_PIECES];
-    }
-    const uint32_t bits = (uint32_t)(plane >> (8 * row)) & 0xFFu;
+__device__ __forceinline__ uint64_t bb_obs_plane(const uint64_t* __restrict__ board, const uint32_t* __restrict__ pieces,
+                                                 const uint64_t* cells, int64_t t) {
+    const int64_t env = t >> (BF16 ? 5 : 6);
+    const int ch = (int)(t >> (BF16 ? 3 : 4)) & 3;
+    if (ch == 0) return __ldg(board + env);
+    const uint32_t pw = __ldg(pieces + env);
+    const uint32_t id = (pw >> (8 * (ch - 1))) & 0xFFu;
+    const bool used = (pw >> (24 + ch - 1)) & 1u;
+    return used ? 0ull : cells[id < BB_NUM_PIECES ? id : BB_NUM_PIECES];
+}
+
+template <bool BF16>
+__device__ __forceinline__ void bb_unpack_obs_item(void* __restrict__ obs, int64_t t, uint64_t plane_bits) {
     if (BF16) {
-        // bf16 1.0 = 0x3F80
-        uint32_t w[4];
+        const uint32_t bits = (uint32_t)(plane_bits >> (8 * ((int)t & 7))) & 0xFFu;
+        uint32_t w[4];                              // bf16 1.0 = 0x3F80
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             w[k] = (((bits >> (2 * k)) & 1u) ? 0x3F80u : 0u) | (((bits >> (2 * k + 1)) & 1u) ? 0x3F800000u : 0u);
         reinterpret_cast<uint4*>(obs)[t] = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-        float4 lo, hi;
-        lo.x = (bits & 1u) ? 1.f : 0.f;  lo.y = (bits & 2u) ? 1.f : 0.f;
-        lo.z = (bits & 4u) ? 1.f : 0.f;  lo.w = (bits & 8u) ? 1.f : 0.f;
-        hi.x = (bits & 16u) ? 1.f : 0.f; hi.y = (bits & 32u) ? 1.f : 0.f;
-        hi.z = (bits & 64u) ? 1.f : 0.f; hi.w = (bits & 128u) ? 1.f : 0.f;
-        float4* o = reinterpret_cast<float4*>(obs) + 2 * t;
-        o[0] = lo;
-        o[1] = hi;
+        const uint32_t bits = (uint32_t)(plane_bits >> (4 * ((int)t & 15))) & 0xFu;   // row*8 + half*4
+        float4 v;
+        v.x = (bits & 1u) ? 1.f : 0.f; v.y = (bits & 2u) ? 1.f : 0.f;
+        v.z = (bits & 4u) ? 1.f : 0.f; v.w = (bits & 8u) ? 1.f : 0.f;
+        reinterpret_cast<float4*>(obs)[t] = v;
     }
+}
+
+// Grid-stride: a few thousand long-lived blocks instead of one short block per 8 envs (CTA
+// launch rate, not HBM, bounded the one-shot version); two independent items per iteration.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+bb_unpack_obs_kernel(const uint64_t* __restrict__ board, const uint32_t* __restrict__ pieces,
+                     void* __restrict__ obs, int64_t n) {
+    __shared__ uint64_t cells[BB_NUM_PIECES + 3];
+    for (int k = threadIdx.x; k < BB_NUM_PIECES + 3; k += blockDim.x) cells[k] = c_piece_cells[k];
+    __syncthreads();
+    const int64_t total = n * (BF16 ? 32 : 64);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + stride < total; t += 2 * stride) {
+        const uint64_t p0 = bb_obs_plane<BF16>(board, pieces, cells, t);
+        const uint64_t p1 = bb_obs_plane<BF16>(board, pieces, cells, t + stride);
+        bb_unpack_obs_item<BF16>(obs, t, p0);
+        bb_unpack_obs_item<BF16>(obs, t + stride, p1);
+    }
+    if (t < total) bb_unpack_obs_item<BF16>(obs, t, bb_obs_plane<BF16>(board, pieces, cells, t));
 }
 
 template <bool F32>
@@ -90,8 +107,10 @@ cudaError_t bb_launch_unpack_obs(const uint64_t* board, const uint32_t* pieces, 
                                  int mask_dtype, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     if (obs_nchw) {
-        const int64_t threads = n * 32;
-        const unsigned grid = (unsigned)((threads + 255) / 256);
+        const int64_t threads = n * (obs_dtype == 1 ? 32 : 64);
+        int64_t blocks = (threads + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;        // grid-stride: 8 resident blocks per SM x 2 waves
+        const unsigned grid = (unsigned)blocks;
         if (obs_dtype == 1) bb_unpack_obs_kernel<true><<<grid, 256, 0, stream>>>(board, pieces, obs_nchw, n);
         else bb_unpack_obs_kernel<false><<<grid, 256, 0, stream>>>(board, pieces, obs_nchw, n);
     }

@@ -293,16 +293,13 @@ class VectorizedBlockBlastEnv:
         return dense.bool()
 
     def sample_valid_actions(self):
-        """wrappers.py:133-136: a uniformly random valid action per env (0 if none).  The
-        draw uses torch's CUDA generator, not numpy's global RNG."""
-        torch = self._torch
-        self._handle.observe(None, None, self._d_mask)
-        logits = torch.zeros((self.num_envs, ACTION_SPACE_SIZE), dtype=torch.float32, device=self._d_mask.device)
+        """wrappers.py:133-136: a uniformly random valid action per env (0 if none), drawn by a
+        Philox-keyed kernel (not numpy's global RNG)."""
         self._sample_ctr = getattr(self, "_sample_ctr", 0) + 1
-        capi.masked_sample(logits, self._d_mask, self.num_envs, self.seed ^ 0x5DEECE66D, self._sample_ctr, 0,
-                           self._d_actions)
         if self.output == "numpy":
-            return self._d_actions.cpu().numpy().astype(np.int64)
+            self._handle.sample_valid_actions(self._sample_ctr, None, self._h_actions)
+            return self._h_actions.numpy().astype(np.int64)
+        self._handle.sample_valid_actions(self._sample_ctr, self._d_actions, None)
         return self._d_actions.clone()
 
     def close(self):

@@ -96,6 +96,14 @@ int bb_env_step(bb_env* env, const int32_t* actions, float* rewards, uint8_t* te
 int bb_env_step_random(bb_env* env, int32_t n_steps, int32_t* actions_out, float* rewards,
                        uint8_t* terminated, uint64_t* mask_out, uint64_t* stats, void* stream);
 
+/* VectorizedBlockBlastEnv.sample_valid_actions (wrappers.py:133-136, block_blast_env.py:318-323):
+ * one uniformly random valid action per env (0 if none), k-th set bit of the mask with
+ * k = mulhi(philox_word, n_valid) on Philox stream 3 keyed by (seed, global env id, call_counter).
+ * The env state is not modified.  actions_out: device i32[n] or NULL; h_actions_out: HOST
+ * i32[n] or NULL (copies and synchronises when given).  At least one must be non-NULL. */
+int bb_env_sample_valid_actions(bb_env* env, uint64_t call_counter, int32_t* actions_out,
+                                int32_t* h_actions_out, void* stream);
+
 /* Packed observation of the current states (engine.get_observation, engine.py:478-507):
  * board_out device u64[n], pieces_out device u32[n], mask_out device u64[3*n]; any NULL. */
 int bb_env_observe(bb_env* env, uint64_t* board_out, uint32_t* pieces_out, uint64_t* mask_out,
