@@ -471,7 +471,8 @@ def main():
 
     # ------------------------------------------------------------------ e2e through the drop-in API
     Ke = args.e2e_steps or min(K, 100)
-    venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n)
+    venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n,
+                                   reuse_buffers=True)
     venv.reset()
     for _ in range(3):
         venv.step(venv.sample_valid_actions())
@@ -522,8 +523,9 @@ def main():
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
                          "launch_us": per_launch_s * 1e6},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "VectorizedBlockBlastEnv(output='numpy'): sample_valid_actions() + step(actions), "
-                                        "pinned host buffers, packed obs expanded lazily on host"},
+                    "steps": Ke, "api": "VectorizedBlockBlastEnv(output='numpy', reuse_buffers=True): sample_valid_actions() + "
+                                        "step(actions); numpy results are zero-copy views of double-buffered pinned memory, "
+                                        "packed obs expanded lazily on host"},
             "clocks": clocks,
             "extra": {"l2_warm_single_batch_env_steps_per_sec": n * kw / (ms_warm * 1e-3),
                       "fused_256_step_launch_env_steps_per_sec": n * 256 / (ms_fused * 1e-3),

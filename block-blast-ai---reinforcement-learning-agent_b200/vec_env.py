@@ -176,7 +176,7 @@ class VectorizedBlockBlastEnv:
     continues, True = that behaviour)."""
 
     def __init__(self, num_envs, seed=None, reward_config=None, *, output="numpy",
-                 global_env_offset=0, reseed_on_reset=False):
+                 global_env_offset=0, reseed_on_reset=False, reuse_buffers=False):
         import torch
         assert output in ("numpy", "torch", "packed")
         self.num_envs = int(num_envs)
@@ -184,6 +184,9 @@ class VectorizedBlockBlastEnv:
         self.output = output
         self.global_env_offset = int(global_env_offset)
         self.reseed_on_reset = bool(reseed_on_reset)
+        # numpy mode: False = every step returns fresh arrays (reference behaviour); True = zero-copy
+        # views of two alternating pinned buffer sets, valid until the second-next step() call
+        self.reuse_buffers = bool(reuse_buffers)
         self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self.observation_space, self.action_space = _spaces()
         self.single_action_space = self.action_space
@@ -203,14 +206,16 @@ class VectorizedBlockBlastEnv:
         if output == "numpy":
             pin = dict(pin_memory=True)
             self._h_actions = torch.zeros(n, dtype=torch.int32, **pin)
-            self._h_rewards = torch.zeros(n, dtype=torch.float32, **pin)
-            self._h_term = torch.zeros(n, dtype=torch.uint8, **pin)
-            self._h_board = torch.zeros(n, dtype=torch.int64, **pin)
-            self._h_pieces = torch.zeros(n, dtype=torch.int32, **pin)
-            self._h_mask = torch.zeros((3, n), dtype=torch.int64, **pin)
-            self._h_ep_score = torch.zeros(n, dtype=torch.int32, **pin)
-            self._h_ep_len = torch.zeros(n, dtype=torch.int32, **pin)
+            self._h_sets = [dict(rewards=torch.zeros(n, dtype=torch.float32, **pin),
+                                 term=torch.zeros(n, dtype=torch.uint8, **pin),
+                                 board=torch.zeros(n, dtype=torch.int64, **pin),
+                                 pieces=torch.zeros(n, dtype=torch.int32, **pin),
+                                 mask=torch.zeros((3, n), dtype=torch.int64, **pin),
+                                 ep_score=torch.zeros(n, dtype=torch.int32, **pin),
+                                 ep_len=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
+            self._h_flip = 0
         self._dones = np.zeros(n, dtype=bool)
+        self._h_actions_np = self._h_actions.numpy() if output == "numpy" else None
 
     # ------------------------------------------------------------------ plumbing
     def _make_handle(self):
@@ -235,13 +240,14 @@ class VectorizedBlockBlastEnv:
 
     def _obs_numpy(self):
         t = self._torch
+        h = self._h_sets[self._h_flip]
         self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
-        self._h_board.copy_(self._d_board, non_blocking=True)
-        self._h_pieces.copy_(self._d_pieces, non_blocking=True)
-        self._h_mask.copy_(self._d_mask, non_blocking=True)
+        h["board"].copy_(self._d_board, non_blocking=True)
+        h["pieces"].copy_(self._d_pieces, non_blocking=True)
+        h["mask"].copy_(self._d_mask, non_blocking=True)
         t.cuda.current_stream().synchronize()
-        return LazyObs(self._h_board.numpy().view(np.uint64).copy(), self._h_pieces.numpy().view(np.uint32).copy(),
-                       self._h_mask.numpy().view(np.uint64).copy())
+        return LazyObs(h["board"].numpy().view(np.uint64).copy(), h["pieces"].numpy().view(np.uint32).copy(),
+                       h["mask"].numpy().view(np.uint64).copy())
 
     # ------------------------------------------------------------------ reference API
     def reset(self, seed=None):
@@ -262,14 +268,18 @@ class VectorizedBlockBlastEnv:
         if self.output == "numpy":
             a = np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions).reshape(-1)
             assert a.shape[0] == n, "expected %d actions" % n
-            self._h_actions.numpy()[:] = a          # int cast like int(action) in wrappers.py:94
-            self._handle.step_host(self._h_actions, self._h_rewards, self._h_term, self._h_board, self._h_pieces,
-                                   self._h_mask, self._h_ep_score, self._h_ep_len)
-            rewards = self._h_rewards.numpy().copy()
-            term = self._h_term.numpy().astype(bool)
-            obs = LazyObs(self._h_board.numpy().view(np.uint64).copy(), self._h_pieces.numpy().view(np.uint32).copy(),
-                          self._h_mask.numpy().view(np.uint64).copy())
-            infos = LazyInfos(self, term, None, self._h_ep_score.numpy().copy(), self._h_ep_len.numpy().copy())
+            if a is not self._h_actions_np:
+                self._h_actions.numpy()[:] = a      # int cast like int(action) in wrappers.py:94
+            self._h_flip ^= 1
+            h = self._h_sets[self._h_flip]
+            self._handle.step_host(self._h_actions, h["rewards"], h["term"], h["board"], h["pieces"], h["mask"],
+                                   h["ep_score"], h["ep_len"])
+            keep = (lambda x: x) if self.reuse_buffers else (lambda x: x.copy())
+            rewards = keep(h["rewards"].numpy())
+            term = h["term"].numpy().view(bool) if self.reuse_buffers else h["term"].numpy().astype(bool)
+            obs = LazyObs(keep(h["board"].numpy().view(np.uint64)), keep(h["pieces"].numpy().view(np.uint32)),
+                          keep(h["mask"].numpy().view(np.uint64)))
+            infos = LazyInfos(self, term, None, keep(h["ep_score"].numpy()), keep(h["ep_len"].numpy()))
             return obs, rewards, term, np.zeros(n, dtype=bool), infos
         if isinstance(actions, torch.Tensor):
             self._d_actions.copy_(actions.reshape(-1), non_blocking=True)
@@ -298,7 +308,8 @@ class VectorizedBlockBlastEnv:
         self._sample_ctr = getattr(self, "_sample_ctr", 0) + 1
         if self.output == "numpy":
             self._handle.sample_valid_actions(self._sample_ctr, None, self._h_actions)
-            return self._h_actions.numpy().astype(np.int64)
+            # reuse_buffers: hand back the pinned int32 buffer itself; step() recognises it and skips the copy
+            return self._h_actions_np if self.reuse_buffers else self._h_actions_np.astype(np.int64)
         self._handle.sample_valid_actions(self._sample_ctr, self._d_actions, None)
         return self._d_actions.clone()
 
