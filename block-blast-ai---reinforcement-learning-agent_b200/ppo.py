@@ -59,6 +59,7 @@ class PPOAgent:
                                          fc_hidden=tuple(self.config.fc_hidden)).to(self.device)
         if self.config.precision == "bf16":
             self.network = self.network.to(memory_format=torch.channels_last)
+            torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the conv algorithms
         dist.broadcast_module(self.network)
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5)
         self.scheduler = None
