@@ -25,6 +25,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod = importlib.import_module("." + _LAZY[name], __name__)
         return getattr(mod, name)
-    if name in ("philox", "capi", "vec_env", "rollout", "ppo", "network", "build", "dist", "train"):
+    if name in ("philox", "capi", "vec_env", "rollout", "ppo", "network", "build", "dist", "train", "evaluate"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -208,3 +208,16 @@ def test_short_training_run_and_checkpoint_keys(torch, tmp_path):
     assert obs["action_mask"][0, act1] == 1 and set(info) == {"log_prob", "entropy", "value"}
     assert a.get_values(obs).shape == (8,)
     v.close()
+
+
+def test_batched_deterministic_evaluation(torch):
+    """scripts/evaluate.py semantics, batched: one episode per env, argmax policy, reproducible."""
+    from bbgpu.evaluate import evaluate
+    from bbgpu.ppo import PPOAgent
+    torch.manual_seed(1)
+    agent = PPOAgent()
+    r1 = evaluate(agent, num_episodes=200, seed=3)
+    r2 = evaluate(agent, num_episodes=200, seed=3)
+    assert r1["finished"] == 200 and np.array_equal(r1["scores"], r2["scores"]) and np.array_equal(r1["lengths"], r2["lengths"])
+    assert 3 < r1["mean_length"] < 60 and r1["min_score"] > 0 and r1["max_score"] >= r1["mean_score"]
+    assert agent.training            # mode restored
