@@ -470,6 +470,21 @@ def main():
     barrier()
     ms_fused = ev0.elapsed_time(ev1)
 
+    # rollout kernel: one launch = 16 steps, EVERY step's actions/rewards/terminated/masks written ([16, N] arrays)
+    S = 16
+    RA = torch.zeros((S, n), dtype=torch.int32, device=dev); RR = torch.zeros((S, n), dtype=torch.float32, device=dev)
+    RT = torch.zeros((S, n), dtype=torch.uint8, device=dev); RM = torch.zeros((S, 3, n), dtype=torch.int64, device=dev)
+    for b in range(2):
+        envs[b].rollout_random(S, RA, RR, RT, RM, stats)
+    barrier()
+    ev0.record()
+    for k in range(32):
+        envs[k % M].rollout_random(S, RA, RR, RT, RM, stats)
+    ev1.record()
+    barrier()
+    ms_roll = ev0.elapsed_time(ev1)
+    del RA, RR, RT, RM
+
     # ------------------------------------------------------------------ e2e through the drop-in API
     Ke = args.e2e_steps or min(K, 100)
     venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n,
@@ -536,6 +551,7 @@ def main():
             "clocks": clocks,
             "extra": {"l2_warm_single_batch_env_steps_per_sec": n * kw / (ms_warm * 1e-3),
                       "fused_256_step_launch_env_steps_per_sec": n * 256 / (ms_fused * 1e-3),
+                      "rollout16_all_outputs_env_steps_per_sec": n * 16 * 32 / (ms_roll * 1e-3),
                       "episodes": s[1], "mean_episode_len": (s[3] / s[1]) if s[1] else None,
                       "mean_final_score": (s[2] / s[1]) if s[1] else None, "wall_s_timed_region": wall},
         }

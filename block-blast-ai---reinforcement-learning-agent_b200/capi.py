@@ -57,6 +57,7 @@ def lib():
     L.bb_env_reset.argtypes = [vp, vp, vp, vp]
     L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.bb_env_rollout_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.bb_env_observe.argtypes = [vp, vp, vp, vp, vp]
     L.bb_env_sample_valid_actions.argtypes = [vp, u64, vp, vp, vp]
     L.bb_env_get_state.argtypes = [vp, vp, vp]
@@ -141,6 +142,11 @@ class EnvHandle:
     def step_random(self, n_steps=1, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
         check(lib().bb_env_step_random(self.h, int(n_steps), ptr(actions_out), ptr(rewards), ptr(terminated),
                                        ptr(mask_out), ptr(stats), current_stream()))
+
+    def rollout_random(self, n_steps, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
+        """n_steps in one launch, outputs of EVERY step written to [n_steps, ...] arrays."""
+        check(lib().bb_env_rollout_random(self.h, int(n_steps), ptr(actions_out), ptr(rewards), ptr(terminated),
+                                          ptr(mask_out), ptr(stats), current_stream()))
 
     def sample_valid_actions(self, call_counter, actions_out=None, h_actions_out=None):
         check(lib().bb_env_sample_valid_actions(self.h, int(call_counter), ptr(actions_out), ptr(h_actions_out),

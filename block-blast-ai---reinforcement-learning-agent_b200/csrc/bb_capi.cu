@@ -119,8 +119,17 @@ int bb_env_step_random(bb_env* e, int32_t n_steps, int32_t* actions_out, float* 
                        uint64_t* mask_out, uint64_t* stats, void* stream) {
     if (!e) return fail(-1, "bb_env_step_random: env is NULL");
     if (n_steps < 1) return fail(-1, "bb_env_step_random: n_steps must be >= 1");
-    BB_CUDA(bb_launch_step_random(e->arr, e->cfg, n_steps, actions_out, rewards, terminated, mask_out,
+    BB_CUDA(bb_launch_step_random(e->arr, e->cfg, n_steps, 0, actions_out, rewards, terminated, mask_out,
                                   (unsigned long long*)stats, (cudaStream_t)stream), "bb_env_step_random launch");
+    return 0;
+}
+
+int bb_env_rollout_random(bb_env* e, int32_t n_steps, int32_t* actions_out, float* rewards, uint8_t* terminated,
+                          uint64_t* mask_out, uint64_t* stats, void* stream) {
+    if (!e) return fail(-1, "bb_env_rollout_random: env is NULL");
+    if (n_steps < 1) return fail(-1, "bb_env_rollout_random: n_steps must be >= 1");
+    BB_CUDA(bb_launch_step_random(e->arr, e->cfg, n_steps, 1, actions_out, rewards, terminated, mask_out,
+                                  (unsigned long long*)stats, (cudaStream_t)stream), "bb_env_rollout_random launch");
     return 0;
 }
 

@@ -238,7 +238,7 @@ __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, c
 // ---------------------------------------------------------------------------------------
 template <bool RANDOM>
 __global__ void __launch_bounds__(BB_STEP_THREADS, BB_STEP_MIN_BLOCKS)
-bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actions, int n_steps,
+bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actions, int n_steps, int per_step,
                int32_t* __restrict__ actions_out, float* __restrict__ rewards,
                uint8_t* __restrict__ terminated, uint64_t* __restrict__ mask_out,
                int32_t* __restrict__ ep_score, int32_t* __restrict__ ep_len,
@@ -289,9 +289,26 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
             bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o);
             if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
         }
+        if (RANDOM && per_step && live) {
+            // rollout mode: every step's outputs go to row `step` of [n_steps][...] arrays
+            const int64_t base = (int64_t)step * E.n + i;
+            if (actions_out) actions_out[base] = action;
+            if (rewards) rewards[base] = o.reward;
+            if (terminated) terminated[base] = (uint8_t)o.terminated;
+            if (mask_out) {
+                const int64_t mb = (int64_t)step * 3 * E.n + i;
+                mask_out[mb] = o.mask[0];
+                mask_out[mb + E.n] = o.mask[1];
+                mask_out[mb + 2 * E.n] = o.mask[2];
+            }
+        }
+    }
+    if (RANDOM && per_step) {
+        if (live) bb_store_state(E, i, s);
+        actions_out = nullptr; rewards = nullptr; terminated = nullptr; mask_out = nullptr;   // already written
     }
     if (live) {
-        bb_store_state(E, i, s);
+        if (!(RANDOM && per_step)) bb_store_state(E, i, s);
         if (RANDOM && actions_out) actions_out[i] = action;
         if (rewards) rewards[i] = o.reward;
         if (terminated) terminated[i] = (uint8_t)o.terminated;
@@ -414,15 +431,15 @@ cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const i
                            float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
                            int32_t* ep_len, uint32_t* info_out, cudaStream_t stream) {
     bb_step_kernel<false><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, actions, 1, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, nullptr);
+        E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, nullptr);
     return cudaGetLastError();
 }
 
-cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps,
+cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps, int per_step,
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
                                   uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream) {
     bb_step_kernel<true><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, nullptr, n_steps, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats);
+        E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats);
     return cudaGetLastError();
 }
 

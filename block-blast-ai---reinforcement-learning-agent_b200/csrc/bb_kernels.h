@@ -25,7 +25,7 @@ struct BBEnvArrays {
 cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const int32_t* actions,
                            float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
                            int32_t* ep_len, uint32_t* info_out, cudaStream_t stream);
-cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps,
+cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps, int per_step,
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
                                   uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream);
 cudaError_t bb_launch_reset(const BBEnvArrays& E, const uint8_t* reset_mask, uint64_t* mask_out, cudaStream_t stream);

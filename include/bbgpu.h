@@ -96,6 +96,15 @@ int bb_env_step(bb_env* env, const int32_t* actions, float* rewards, uint8_t* te
 int bb_env_step_random(bb_env* env, int32_t n_steps, int32_t* actions_out, float* rewards,
                        uint8_t* terminated, uint64_t* mask_out, uint64_t* stats, void* stream);
 
+/* Random-policy ROLLOUT: the same n_steps as bb_env_step_random in one launch (state in
+ * registers), but every step's outputs are written: actions_out i32[n_steps][n], rewards
+ * f32[n_steps][n], terminated u8[n_steps][n], mask_out u64[n_steps][3][n] (mask of the state
+ * AFTER that step); any may be NULL.  Row t equals what bb_env_step_random(1) would have
+ * produced at step t.  The data-collection form of the sample_valid_actions + step loop
+ * (scripts/benchmark.py:127-129). */
+int bb_env_rollout_random(bb_env* env, int32_t n_steps, int32_t* actions_out, float* rewards,
+                          uint8_t* terminated, uint64_t* mask_out, uint64_t* stats, void* stream);
+
 /* VectorizedBlockBlastEnv.sample_valid_actions (wrappers.py:133-136, block_blast_env.py:318-323):
  * one uniformly random valid action per env (0 if none), k-th set bit of the mask with
  * k = mulhi(philox_word, n_valid) on Philox stream 3 keyed by (seed, global env id, call_counter).

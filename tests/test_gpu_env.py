@@ -263,3 +263,25 @@ def test_full_size_properties_262144_envs(torch):
     torch.cuda.synchronize()
     assert h2.get_state().tobytes() == st.tobytes()
     h.close(); h2.close()
+
+
+def test_rollout_kernel_equals_step_by_step(torch):
+    """bb_env_rollout_random: one launch, every step's outputs materialised."""
+    from bbgpu import capi
+    n, S, seed = 5000, 24, 13
+    a, b = capi.EnvHandle(n, seed), capi.EnvHandle(n, seed)
+    A = torch.zeros((S, n), dtype=torch.int32, device="cuda")
+    R = torch.zeros((S, n), dtype=torch.float32, device="cuda")
+    Tm = torch.zeros((S, n), dtype=torch.uint8, device="cuda")
+    M = torch.zeros((S, 3, n), dtype=torch.int64, device="cuda")
+    st1 = torch.zeros(4, dtype=torch.int64, device="cuda")
+    st2 = torch.zeros(4, dtype=torch.int64, device="cuda")
+    a.rollout_random(S, A, R, Tm, M, st1)
+    B = _dev_buffers(torch, n)
+    for t in range(S):
+        b.step_random(1, B["actions"], B["rewards"], B["term"], B["mask"], st2)
+        assert torch.equal(A[t], B["actions"]) and torch.equal(Tm[t], B["term"]) and torch.equal(M[t], B["mask"]), t
+        assert torch.equal(R[t].view(torch.int32), B["rewards"].view(torch.int32)), t
+    torch.cuda.synchronize()
+    assert a.get_state().tobytes() == b.get_state().tobytes() and st1.tolist() == st2.tolist()
+    a.close(); b.close()
