@@ -78,3 +78,42 @@ def test_product_has_no_oracle_import():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "bboracle" not in src, f
+
+
+def test_c_abi_error_paths_return_codes_not_crashes(libpath):
+    """Argument errors are reported through return codes + bb_last_error() before any CUDA call
+    (so this runs without a GPU); invalid ACTIONS are not errors (block_blast_env.py:240-245)."""
+    lib = C.CDLL(libpath)
+    lib.bb_last_error.restype = C.c_char_p
+    vp, i64, u64, u32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32
+    lib.bb_env_create.argtypes = [C.POINTER(vp), i64, u64, i64, vp, u32]
+    h = vp()
+    assert lib.bb_env_create(None, 8, 0, 0, None, 0) < 0 and b"out is NULL" in lib.bb_last_error()
+    assert lib.bb_env_create(C.byref(h), 0, 0, 0, None, 0) < 0 and b"n_envs" in lib.bb_last_error()
+    assert lib.bb_env_create(C.byref(h), -5, 0, 0, None, 0) < 0
+    assert lib.bb_env_create(C.byref(h), 8, 0, -1, None, 0) < 0 and b"offset" in lib.bb_last_error()
+    assert h.value is None
+    lib.bb_env_step.argtypes = [vp] * 9
+    assert lib.bb_env_step(None, None, None, None, None, None, None, None, None) < 0 and b"env is NULL" in lib.bb_last_error()
+    lib.bb_env_reset.argtypes = [vp] * 4
+    assert lib.bb_env_reset(None, None, None, None) < 0
+    lib.bb_env_step_random.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    assert lib.bb_env_step_random(None, 1, None, None, None, None, None, None) < 0
+    lib.bb_env_destroy.argtypes = [vp]
+    assert lib.bb_env_destroy(None) == 0                      # destroying nothing is fine
+    lib.bb_env_num_envs.argtypes = [vp]
+    lib.bb_env_num_envs.restype = i64
+    assert lib.bb_env_num_envs(None) == -1
+    lib.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
+    assert lib.bb_gae(None, None, None, None, 0.99, 0.95, None, None, None, 4, 4, None) < 0 and b"NULL" in lib.bb_last_error()
+    assert lib.bb_gae(None, None, None, None, 0.99, 0.95, None, None, None, -1, 4, None) < 0
+    lib.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
+    assert lib.bb_masked_sample(None, 0, None, 0, 0, 0, 0, None, None, None, 4, None) < 0
+    one = (C.c_char * 64)()
+    assert lib.bb_masked_sample(one, 7, one, 1, 0, 0, 0, one, None, None, 0, None) < 0 and b"dtype" in lib.bb_last_error()
+    assert lib.bb_masked_sample(one, 0, one, 1, 0, 0, 9, one, None, None, 0, None) < 0 and b"mode" in lib.bb_last_error()
+    lib.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
+    assert lib.bb_unpack_obs(None, None, None, 0, one, 0, None, 0, 1, None) < 0          # obs without board/pieces
+    assert lib.bb_unpack_obs(one, one, one, 1, one, 5, None, 0, 1, None) < 0 and b"obs_dtype" in lib.bb_last_error()
+    assert lib.bb_unpack_obs(one, one, None, 1, None, 0, one, 2, 1, None) < 0           # dense mask without mask
+    assert lib.bb_unpack_obs(one, one, one, 1, None, 0, None, 0, -3, None) < 0

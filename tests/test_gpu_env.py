@@ -285,3 +285,32 @@ def test_rollout_kernel_equals_step_by_step(torch):
     torch.cuda.synchronize()
     assert a.get_state().tobytes() == b.get_state().tobytes() and st1.tolist() == st2.tolist()
     a.close(); b.close()
+
+
+def test_config4_size_and_tiny_sizes(torch):
+    """1,048,576 envs (BASELINE config 4's total) on one GPU, and the 1-env / odd-size corners."""
+    from bbgpu import capi
+    n = 1_048_576
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    h = capi.EnvHandle(n, 7)
+    h.step_random(20, None, None, None, None, stats)
+    torch.cuda.synchronize()
+    s = stats.cpu().tolist()
+    assert s[0] == n * 20 and s[1] > n // 2          # ~1 episode per 14.7 steps per env
+    st = h.get_state()
+    assert int(st["moves"].max()) <= 20 and int(st["policy_ctr"].min()) == 20 == int(st["policy_ctr"].max())
+    h.close()
+    for m in (1, 31, 33, 129):
+        a = capi.EnvHandle(m, 3)
+        B = _dev_buffers(torch, m)
+        a.step_random(50, B["actions"], B["rewards"], B["term"], B["mask"], None)
+        torch.cuda.synchronize()
+        big = capi.EnvHandle(200, 3)
+        big.step_random(50)
+        torch.cuda.synchronize()
+        assert a.get_state().tobytes() == big.get_state()[:m].tobytes()      # same global ids -> same trajectories
+        a.close(); big.close()
+    # empty GAE / sample calls are no-ops
+    e = torch.zeros((0, 8), device="cuda")
+    capi.gae(e, e, e, torch.zeros(8, device="cuda"), 0.99, 0.95, e, e, None)
+    torch.cuda.synchronize()
