@@ -243,6 +243,9 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
 int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask, int64_t mask_stride,
                   void* obs_nchw, int obs_dtype, void* mask_dense, int mask_dtype, int64_t n, void* stream) {
     if (n < 0) return fail(-1, "bb_unpack_obs: negative n");
+    if (obs_nchw && obs_dtype != BB_F32 && obs_dtype != BB_BF16) return fail(-1, "bb_unpack_obs: obs_dtype must be BB_F32 or BB_BF16");
+    if (mask_dense && mask_dtype != BB_F32 && mask_dtype != BB_U8) return fail(-1, "bb_unpack_obs: mask_dtype must be BB_F32 or BB_U8");
+    if (n == 0) return 0;
     if (obs_nchw && (!board || !pieces)) return fail(-1, "bb_unpack_obs: board/pieces required for obs");
     if (obs_nchw && obs_dtype != BB_F32 && obs_dtype != BB_BF16) return fail(-1, "bb_unpack_obs: obs_dtype must be BB_F32 or BB_BF16");
     if (mask_dense && !mask) return fail(-1, "bb_unpack_obs: mask required for mask_dense");
@@ -256,6 +259,9 @@ int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
                      uint64_t seed, uint64_t call_counter, int mode, int32_t* action, float* logp,
                      float* entropy, int64_t n, void* stream) {
     if (n < 0) return fail(-1, "bb_masked_sample: negative n");
+    if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_masked_sample: logits_dtype must be BB_F32 or BB_BF16");
+    if (mode < 0 || mode > 2) return fail(-1, "bb_masked_sample: mode must be 0, 1 or 2");
+    if (n == 0) return 0;
     if (!logits || !mask || !action) return fail(-1, "bb_masked_sample: logits/mask/action are required");
     if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_masked_sample: logits_dtype must be BB_F32 or BB_BF16");
     if (mode < 0 || mode > 2) return fail(-1, "bb_masked_sample: mode must be 0, 1 or 2");
@@ -267,6 +273,7 @@ int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
 int bb_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
            double gamma, double lam, float* adv, float* ret, double* moments, int64_t T, int64_t N, void* stream) {
     if (T < 0 || N < 0) return fail(-1, "bb_gae: negative size");
+    if (T == 0 || N == 0) return 0;                 // empty rollout: nothing to do (pointers may be NULL)
     if (!rewards || !values || !dones || !last_values || !adv || !ret) return fail(-1, "bb_gae: NULL array");
     // numpy casts the Python doubles gamma and gamma*lambda to float32 before the array multiply
     BB_CUDA(bb_launch_gae(rewards, values, dones, last_values, (float)gamma, (float)(gamma * lam), adv, ret, moments,
