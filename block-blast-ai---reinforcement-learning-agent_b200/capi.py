@@ -65,6 +65,7 @@ def lib():
     L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
     L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
+    L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
     L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     if L.bb_version() != ABI_VERSION:
         raise BBGpuError("libbbgpu.so ABI %d != expected %d" % (L.bb_version(), ABI_VERSION))
@@ -187,6 +188,14 @@ def masked_sample(logits, mask, mask_stride, seed, call_counter, mode, action, l
     check(lib().bb_masked_sample(ptr(logits), dt, ptr(mask), int(mask_stride), int(seed) & (2 ** 64 - 1),
                                  int(call_counter), int(mode), ptr(action), ptr(logp), ptr(entropy), n,
                                  current_stream()))
+
+
+def masked_head_backward(logits, mask, mask_stride, action, grad_logp, grad_entropy, grad_logits):
+    import torch
+    n = logits.shape[0]
+    dt = BB_BF16 if logits.dtype == torch.bfloat16 else BB_F32
+    check(lib().bb_masked_head_backward(ptr(logits), dt, ptr(mask), int(mask_stride), ptr(action), ptr(grad_logp),
+                                        ptr(grad_entropy), ptr(grad_logits), n, current_stream()))
 
 
 def gae(rewards, values, dones, last_values, gamma, lam, adv, ret, moments=None):

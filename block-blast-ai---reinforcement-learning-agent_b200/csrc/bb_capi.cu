@@ -270,6 +270,18 @@ int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
     return 0;
 }
 
+int bb_masked_head_backward(const void* logits, int logits_dtype, const uint64_t* mask, int64_t mask_stride,
+                            const int32_t* action, const float* grad_logp, const float* grad_entropy,
+                            void* grad_logits, int64_t n, void* stream) {
+    if (n < 0) return fail(-1, "bb_masked_head_backward: negative n");
+    if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_masked_head_backward: logits_dtype must be BB_F32 or BB_BF16");
+    if (n == 0) return 0;
+    if (!logits || !mask || !action || !grad_logp || !grad_logits) return fail(-1, "bb_masked_head_backward: NULL array");
+    BB_CUDA(bb_launch_masked_head_bwd(logits, logits_dtype, mask, mask_stride, action, grad_logp, grad_entropy, grad_logits,
+                                      n, (cudaStream_t)stream), "bb_masked_head_backward launch");
+    return 0;
+}
+
 int bb_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
            double gamma, double lam, float* adv, float* ret, double* moments, int64_t T, int64_t N, void* stream) {
     if (T < 0 || N < 0) return fail(-1, "bb_gae: negative size");

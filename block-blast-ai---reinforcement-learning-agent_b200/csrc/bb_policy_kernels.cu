@@ -285,3 +285,110 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
         bb_masked_sample_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------ K3 backward
+// Gradient of (log_prob[action], masked entropy) w.r.t. the raw logits, for the PPO update
+// (autograd of src/models/network.py:210-262 as used at src/agents/ppo.py:366-392):
+//   d log_prob / d z_i = [eps <= p_a <= 1-eps] (delta_ia - p_i)        (Categorical clamps p)
+//   d entropy  / d z_i = -p_i (log p_i + H)
+// for valid actions i, 0 for masked ones.  Same 8-lanes-per-row layout as the forward; p is
+// recomputed from the logits (768 B read + 768 B written per row, nothing saved between passes).
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
+                          const int32_t* __restrict__ action, const float* __restrict__ g_logp,
+                          const float* __restrict__ g_ent, void* __restrict__ dlogits, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & 7;
+    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = row_raw < n;
+    const int64_t row = live ? row_raw : n - 1;
+    float z[24];
+    uint32_t mb = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const uint64_t w = __ldg(mask + (int64_t)p * stride + row);
+        mb |= ((uint32_t)(w >> (4 * l)) & 0xFu) << (8 * p);
+        mb |= ((uint32_t)(w >> (32 + 4 * l)) & 0xFu) << (8 * p + 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        float4 v;
+        if (BF16) {
+            const uint2 h = reinterpret_cast<const uint2*>(logits)[row * 48 + k * 8 + l];
+            v.x = __uint_as_float(h.x << 16); v.y = __uint_as_float(h.x & 0xFFFF0000u);
+            v.z = __uint_as_float(h.y << 16); v.w = __uint_as_float(h.y & 0xFFFF0000u);
+        } else {
+            v = reinterpret_cast<const float4*>(logits)[row * 48 + k * 8 + l];
+        }
+        z[4 * k + 0] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) m = fmaxf(m, ((mb >> i) & 1u) ? z[i] : -INFINITY);
+    m = grp_max(m);
+    const bool any_valid = m > -INFINITY;
+    float s = 0.f, sz = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const bool ok = (mb >> i) & 1u;
+        const float d = ok ? z[i] - m : 0.f;
+        const float e = ok ? exp2f(d * K3_LOG2E) : 0.f;
+        s += e;
+        sz = fmaf(e, d, sz);
+        z[i] = d;                                   // keep z - m (0 where masked)
+    }
+    s = grp_sum(s);
+    sz = grp_sum(sz);
+    const float inv = any_valid ? __frcp_rn(s) : 0.f;
+    const float logS = any_valid ? logf(s) : 0.f;
+    const float H = logS - sz * inv;                // masked entropy
+    const int act = action[row];
+    const int slot = ((act >> 5) << 2) | (act & 3);
+    const bool own = act >= 0 && act < 192 && ((act & 31) >> 2) == l;
+    // p_a for the clamp indicator
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) mine += (own && i == slot && ((mb >> i) & 1u)) ? exp2f(z[i] * K3_LOG2E) * inv : 0.f;
+    const float pa = grp_sum(mine);
+    const float eps = 1.1920928955078125e-07f;
+    const float g1 = (pa >= eps && pa <= 1.f - eps) ? g_logp[row] : 0.f;
+    const float g2 = g_ent ? g_ent[row] : 0.f;
+    float out[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const bool ok = (mb >> i) & 1u;
+        const float p = ok ? exp2f(z[i] * K3_LOG2E) * inv : 0.f;
+        const float logp = z[i] - logS;             // log p_i for valid i
+        float g = -g1 * p - g2 * p * (logp + H);
+        if (own && i == slot) g += g1;
+        out[i] = ok ? g : 0.f;
+    }
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (BF16) {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(out[4 * k], out[4 * k + 1]);
+            const __nv_bfloat162 b = __floats2bfloat162_rn(out[4 * k + 2], out[4 * k + 3]);
+            uint2 h;
+            h.x = *reinterpret_cast<const uint32_t*>(&a);
+            h.y = *reinterpret_cast<const uint32_t*>(&b);
+            reinterpret_cast<uint2*>(dlogits)[row * 48 + k * 8 + l] = h;
+        } else {
+            reinterpret_cast<float4*>(dlogits)[row * 48 + k * 8 + l] =
+                make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+        }
+    }
+}
+
+cudaError_t bb_launch_masked_head_bwd(const void* logits, int dtype, const uint64_t* mask, int64_t mask_stride,
+                                      const int32_t* action, const float* g_logp, const float* g_ent,
+                                      void* dlogits, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n * 8 + 127) / 128);
+    if (dtype == 1)
+        bb_masked_head_bwd_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n);
+    else
+        bb_masked_head_bwd_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n);
+    return cudaGetLastError();
+}

@@ -36,6 +36,7 @@ class PPOConfig:
     conv_channels: Tuple[int, ...] = (64, 128, 128)
     fc_hidden: Tuple[int, ...] = (512, 256)
     precision: str = "fp32"          # "fp32" (reference numerics) | "bf16" (autocast, channels_last)
+    fused_head: bool = True          # PPO update: K3 forward + fused backward kernel instead of torch ops
 
     def to_dict(self):
         return {f.name: getattr(self, f.name) for f in fields(self)}
@@ -152,12 +153,16 @@ class PPOAgent:
         sums = torch.zeros(6, dtype=torch.float64, device=self.device)
         n_updates = 0
         self.bucket.rebind()
+        fused = cfg.fused_head and buffer.piece_planes is None
         for _ in range(cfg.num_epochs):
-            for obs, mask, actions, old_logp, adv, ret in buffer.iter_minibatches(cfg.batch_size):
+            for obs, mask, actions, old_logp, adv, ret in buffer.iter_minibatches(cfg.batch_size, packed_mask=fused):
                 if cfg.precision == "bf16":
                     obs = obs.contiguous(memory_format=torch.channels_last)
                 with self._autocast():
-                    _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
+                    if fused:       # mask = int64 planes [3,B]
+                        _, new_logp, entropy, values = self.network.evaluate_actions_fused(obs, mask, actions)
+                    else:
+                        _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
                 values = values.float()
                 ratio = torch.exp(new_logp - old_logp)
                 surr1 = ratio * adv
@@ -184,7 +189,7 @@ class PPOAgent:
     # ------------------------------------------------------------------ persistence / modes
     def save(self, path):
         """Same keys as ppo.py:425-431 so the reference's evaluate.py / GUI can load it."""
-        cfgd = {k: v for k, v in self.config.to_dict().items() if k != "precision"}
+        cfgd = {k: v for k, v in self.config.to_dict().items() if k not in ("precision", "fused_head")}
         torch.save({"network_state_dict": self.network.state_dict(),
                     "optimizer_state_dict": self.optimizer.state_dict(), "config": cfgd}, path)
 
@@ -194,7 +199,8 @@ class PPOAgent:
         if "optimizer_state_dict" in ck:
             self.optimizer.load_state_dict(ck["optimizer_state_dict"])
         if "config" in ck:
-            self.config = PPOConfig.from_dict({**ck["config"], "precision": self.config.precision})
+            self.config = PPOConfig.from_dict({**ck["config"], "precision": self.config.precision,
+                                               "fused_head": self.config.fused_head})
         self.bucket.rebind()
 
     def train(self):

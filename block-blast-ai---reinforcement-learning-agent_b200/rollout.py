@@ -125,14 +125,18 @@ class RolloutBuffer:
         return mean.float(), var.sqrt().float()
 
     # ------------------------------------------------------------------ minibatches
-    def _expand(self, idx):
-        """Gather samples idx (flat over T*N) and expand them to (B,4,8,8) f32 + (B,192) f32."""
+    def _expand(self, idx, packed_mask=False):
+        """Gather samples idx (flat over T*N) and expand them to (B,4,8,8) f32 + (B,192) f32
+        (or, with packed_mask, the int64 [3,B] mask planes the fused head consumes)."""
         n = idx.numel()
         T, N = self.buffer_size, self.num_envs
         boards = self.boards.view(-1)[idx]
         t_i, n_i = idx // N, idx % N
         masks = self.action_masks[t_i, :, n_i].t().contiguous()            # [3,B]
         obs = torch.empty((n, 4, 8, 8), dtype=torch.float32, device=self.device)
+        if packed_mask and self.piece_planes is None:
+            capi.unpack_obs(boards, self.pieces.view(-1)[idx], masks, n, obs=obs, mask_dense=None, n=n)
+            return obs, masks
         dense = torch.empty((n, 192), dtype=torch.float32, device=self.device)
         if self.piece_planes is None:
             pieces = self.pieces.view(-1)[idx]
@@ -148,16 +152,16 @@ class RolloutBuffer:
                 obs[:, 1 + k] = tmp[:, 0]
         return obs, dense
 
-    def iter_minibatches(self, batch_size, generator=None):
-        """Fast path: yields (obs_nchw f32 (B,4,8,8), mask f32 (B,192), actions i64, old_log_probs,
-        normalised advantages, returns), all CUDA tensors."""
+    def iter_minibatches(self, batch_size, generator=None, packed_mask=False):
+        """Fast path: yields (obs_nchw f32 (B,4,8,8), mask f32 (B,192) [or int64 planes [3,B] with
+        packed_mask], actions i64, old_log_probs, normalised advantages, returns), all CUDA tensors."""
         total = self.buffer_size * self.num_envs
         mean, std = self.advantage_mean_std()
         adv = (self.advantages.view(-1) - mean) / (std + 1e-8)
         perm = torch.randperm(total, device=self.device, generator=generator)
         for start in range(0, total, batch_size):
             idx = perm[start:start + batch_size]
-            obs, dense = self._expand(idx)
+            obs, dense = self._expand(idx, packed_mask and self.piece_planes is None)
             yield (obs, dense, self.actions.view(-1)[idx].long(), self.log_probs.view(-1)[idx], adv[idx],
                    self.returns.view(-1)[idx])
 

@@ -159,6 +159,15 @@ int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
                      int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
                      int32_t* action, float* logp, float* entropy, int64_t n, void* stream);
 
+/* Backward of bb_masked_sample(mode 2) for the PPO update: autograd of log_prob[action] and the
+ * masked entropy through softmax / Categorical (network.py:210-262 as differentiated at
+ * src/agents/ppo.py:366-395).  grad_logits[n,192] (same dtype as logits) =
+ *   grad_logp * [eps <= p_a <= 1-eps] * (onehot(action) - p)  -  grad_entropy * p * (log p + H),
+ * zero at masked actions.  grad_entropy may be NULL. */
+int bb_masked_head_backward(const void* logits, int logits_dtype, const uint64_t* mask,
+                            int64_t mask_stride, const int32_t* action, const float* grad_logp,
+                            const float* grad_entropy, void* grad_logits, int64_t n, void* stream);
+
 /* GAE and returns (RolloutBuffer.compute_returns_and_advantages, src/agents/ppo.py:141-169),
  * reverse scan over T, float32, same operation order as the reference (bit-identical).
  *   rewards, values, dones: device f32[T*N] time-major; last_values device f32[N]

@@ -196,3 +196,42 @@ def test_sampling_is_valid_reproducible_and_distributed_like_softmax(torch):
     capi.masked_sample(logits, planes, n, 99, 8, 0, a2, None, None)
     torch.cuda.synchronize()
     assert (a2.cpu().numpy() != s).mean() > 0.5
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_fused_head_backward_matches_torch_autograd(torch, dtype):
+    """MaskedHead (K3 forward + bb_masked_head_backward) against autograd through the torch
+    restatement of network.py:210-262 (which tests/test_ppo_host.py pins to the reference)."""
+    from bbgpu.network import BlockBlastNetwork, MaskedHead, _pack_mask_planes
+    torch.manual_seed(3)
+    n = 4096
+    dt = getattr(torch, dtype)
+    base = (torch.randn(n, 192, device="cuda") * 3).to(dt)
+    dense = (torch.rand(n, 192, device="cuda") < torch.rand(n, 1, device="cuda") * 0.6)
+    dense[torch.arange(n), torch.randint(0, 192, (n,))] = True
+    dense[0] = False; dense[0, 17] = True                       # single valid action: p = 1 -> clamp kills the gradient
+    act = (torch.rand(n, 192, device="cuda") * dense).argmax(1)
+    w1, w2 = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    planes = _pack_mask_planes(dense)
+
+    def ref(logits):
+        probs = torch.softmax(logits.float().masked_fill(~dense, float("-inf")), -1)
+        eps = torch.finfo(torch.float32).eps
+        pn = probs / probs.sum(-1, keepdim=True)
+        lp = torch.log(pn.clamp(eps, 1 - eps)).gather(1, act.unsqueeze(1)).squeeze(1)
+        q = probs / probs.sum(-1, keepdim=True).clamp(min=1e-10)
+        ent = -(q * torch.log(q.clamp(min=1e-10)) * dense).sum(-1)
+        return lp, ent
+
+    a = base.clone().requires_grad_(True)
+    lp_r, en_r = ref(a)
+    (w1 * lp_r + w2 * en_r).sum().backward()
+    b = base.clone().requires_grad_(True)
+    lp_f, en_f = MaskedHead.apply(b, planes, act)
+    (w1 * lp_f + w2 * en_f).sum().backward()
+    torch.testing.assert_close(lp_f, lp_r, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(en_f, en_r, rtol=1e-5, atol=2e-6)
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == "bfloat16" else dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(b.grad.float(), a.grad.float(), **tol)
+    assert (b.grad[~dense] == 0).all() and b.grad.dtype == dt
+    assert float(b.grad[0].abs().sum()) == 0.0                   # clamped at 1 - eps, like torch
