@@ -324,13 +324,14 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         if (info_out) info_out[i] = o.info;
     }
     if (RANDOM && stats) {
-        // warp-reduce, one atomic per warp per counter
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            st_eps += __shfl_down_sync(0xffffffffu, st_eps, d);
-            st_score += __shfl_down_sync(0xffffffffu, st_score, d);
-            st_len += __shfl_down_sync(0xffffffffu, st_len, d);
-        }
+        // warp-reduce (redux.sync on the 32-bit halves), one atomic per warp per counter
+        const unsigned FULLM = 0xffffffffu;
+        st_eps = __reduce_add_sync(FULLM, (unsigned)st_eps);
+        // 20-bit limbs so that the 32-lane sums cannot wrap
+        st_score = (unsigned long long)__reduce_add_sync(FULLM, (unsigned)(st_score & 0xFFFFFull)) +
+                   ((unsigned long long)__reduce_add_sync(FULLM, (unsigned)((st_score >> 20) & 0xFFFFFull)) << 20) +
+                   ((unsigned long long)__reduce_add_sync(FULLM, (unsigned)(st_score >> 40)) << 40);
+        st_len = __reduce_add_sync(FULLM, (unsigned)st_len);
         const unsigned long long nlive = __popc(__ballot_sync(0xffffffffu, live));
         if ((threadIdx.x & 31) == 0) {
 #ifdef BB_PROFILE

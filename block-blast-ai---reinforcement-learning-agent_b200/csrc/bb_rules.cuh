@@ -643,7 +643,10 @@ BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTab
         o.ep_len = s.moves;
         if (!(flags & BB_FLAG_NO_AUTO_RESET)) {
             bb_reset_state(s, seed, env_id, flags);
-            bb_action_mask(s, T, o.mask);
+            // empty board, nothing used: every in-bounds anchor is valid
+            o.mask[0] = T->inb[s.pieces & 0xFFu];
+            o.mask[1] = T->inb[(s.pieces >> 8) & 0xFFu];
+            o.mask[2] = T->inb[(s.pieces >> 16) & 0xFFu];
         }
     }
 }
