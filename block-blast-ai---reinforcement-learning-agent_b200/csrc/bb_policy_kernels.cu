@@ -40,13 +40,13 @@ __device__ __forceinline__ void bb_unpack_obs_item(void* __restrict__ obs, int64
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             w[k] = (((bits >> (2 * k)) & 1u) ? 0x3F80u : 0u) | (((bits >> (2 * k + 1)) & 1u) ? 0x3F800000u : 0u);
-        reinterpret_cast<uint4*>(obs)[t] = make_uint4(w[0], w[1], w[2], w[3]);
+        __stcs(reinterpret_cast<uint4*>(obs) + t, make_uint4(w[0], w[1], w[2], w[3]));   // streaming: written once
     } else {
         const uint32_t bits = (uint32_t)(plane_bits >> (4 * ((int)t & 15))) & 0xFu;   // row*8 + half*4
         float4 v;
         v.x = (bits & 1u) ? 1.f : 0.f; v.y = (bits & 2u) ? 1.f : 0.f;
         v.z = (bits & 4u) ? 1.f : 0.f; v.w = (bits & 8u) ? 1.f : 0.f;
-        reinterpret_cast<float4*>(obs)[t] = v;
+        __stcs(reinterpret_cast<float4*>(obs) + t, v);
     }
 }
 
@@ -62,13 +62,17 @@ bb_unpack_obs_kernel(const uint64_t* __restrict__ board, const uint32_t* __restr
     const int64_t total = n * (BF16 ? 32 : 64);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; t + stride < total; t += 2 * stride) {
+    for (; t + 3 * stride < total; t += 4 * stride) {
         const uint64_t p0 = bb_obs_plane<BF16>(board, pieces, cells, t);
         const uint64_t p1 = bb_obs_plane<BF16>(board, pieces, cells, t + stride);
+        const uint64_t p2 = bb_obs_plane<BF16>(board, pieces, cells, t + 2 * stride);
+        const uint64_t p3 = bb_obs_plane<BF16>(board, pieces, cells, t + 3 * stride);
         bb_unpack_obs_item<BF16>(obs, t, p0);
         bb_unpack_obs_item<BF16>(obs, t + stride, p1);
+        bb_unpack_obs_item<BF16>(obs, t + 2 * stride, p2);
+        bb_unpack_obs_item<BF16>(obs, t + 3 * stride, p3);
     }
-    if (t < total) bb_unpack_obs_item<BF16>(obs, t, bb_obs_plane<BF16>(board, pieces, cells, t));
+    for (; t < total; t += stride) bb_unpack_obs_item<BF16>(obs, t, bb_obs_plane<BF16>(board, pieces, cells, t));
 }
 
 template <bool F32>
@@ -135,6 +139,13 @@ cudaError_t bb_launch_unpack_obs(const uint64_t* board, const uint32_t* pieces, 
 // Sampling is the inverse CDF of u * sum(p) over the order (lane, k, c) — a fixed permutation
 // of the actions, so the draw is an exact categorical sample; philox.py documents the order.
 #define K3_LOG2E 1.4426950408889634f
+#define K3_DMIN (-150.0f)     // exp2(-150 * log2e) == 0 in float32: masked and hopeless actions alike
+
+__device__ __forceinline__ float k3_ex2(float x) {      // 2^x, one MUFU (rel. error 2^-22)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ float grp_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -180,16 +191,20 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
     }
     float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) m = fmaxf(m, ((mb >> i) & 1u) ? z[i] : -INFINITY);
+    for (int i = 0; i < 24; ++i) {
+        z[i] = ((mb >> i) & 1u) ? z[i] : -INFINITY;               // -inf masking (network.py:175-180)
+        m = fmaxf(m, z[i]);
+    }
     m = grp_max(m);
     const bool any_valid = m > -INFINITY;
+    const float mm = any_valid ? m : 0.f;
     float s = 0.f, sz = 0.f;
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
-        const float d = z[i] - m;                                 // <= 0 for valid actions
-        const float e = ((mb >> i) & 1u) ? exp2f(d * K3_LOG2E) : 0.f;
+        const float d = fmaxf(z[i] - mm, K3_DMIN);                 // <= 0; clamped so that 0 * d stays 0
+        const float e = k3_ex2(d * K3_LOG2E);                      // exactly 0 for masked actions
         s += e;
-        sz = fmaf(e, ((mb >> i) & 1u) ? d : 0.f, sz);
+        sz = fmaf(e, d, sz);
         z[i] = e;                                                  // z now holds exp(z - m)
     }
     s = grp_sum(s);
@@ -247,16 +262,36 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         const unsigned nz = (__ballot_sync(0xffffffffu, lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
         // rounding can leave t >= total: fall back to the last lane with mass
         const int L = hit ? (__ffs((int)hit) - 1) : (nz ? (31 - __clz((int)nz)) : 0);
-        // inside lane L: first element whose running sum exceeds t, else its last non-zero one
-        float run = excl;
-        int pick = -1, lastnz = 0;
-        float ppick = 0.f, plast = 0.f;
+        // inside lane L: first element whose running sum exceeds t, else its last non-zero one;
+        // first the 4-action chunk, then the action inside it
+        float c4[6];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            run += z[i];
-            if (z[i] > 0.f) { lastnz = i; plast = z[i]; if (pick < 0 && run > t) { pick = i; ppick = z[i]; } }
+        for (int k = 0; k < 6; ++k) c4[k] = (z[4 * k] + z[4 * k + 1]) + (z[4 * k + 2] + z[4 * k + 3]);
+        float run = excl;
+        int kc = -1, klast = 0;
+        float runc = excl, runlast = excl;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (c4[k] > 0.f) { klast = k; runlast = run; if (kc < 0 && run + c4[k] > t) { kc = k; runc = run; } }
+            run += c4[k];
+        }
+        if (kc < 0) { kc = klast; runc = runlast; }
+        float e4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            e4[c] = z[c];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) e4[c] = kc == k ? z[4 * k + c] : e4[c];
+        }
+        int pick = -1, lastnz = 0;
+        float ppick = 0.f, plast = 0.f, r2 = runc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            r2 += e4[c];
+            if (e4[c] > 0.f) { lastnz = c; plast = e4[c]; if (pick < 0 && r2 > t) { pick = c; ppick = e4[c]; } }
         }
         if (pick < 0) { pick = lastnz; ppick = plast; }
+        pick += 4 * kc;
         const int idx = 32 * (pick >> 2) + 4 * l + (pick & 3);
         const int src = (lane & 24) | L;
         act = __shfl_sync(0xffffffffu, idx, src);
