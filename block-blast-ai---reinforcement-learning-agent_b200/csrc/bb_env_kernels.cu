@@ -69,21 +69,20 @@ __device__ __forceinline__ uint64_t bb_shfl64(uint64_t v, int src) {
 //      are exactly those of the sequential loop.
 // All 32 lanes of the warp must call this (lanes without work pass pending = false).
 // ---------------------------------------------------------------------------------------
+// Phase timers for tools/profile_phases.py (-DBB_PROFILE); BB_PF(...) vanishes in normal builds.
 #ifdef BB_PROFILE
-#define BB_PROF_DECL long long pf_cls = 0, pf_team = 0, pf_rounds = 0, pf_iters = 0;
+struct BBProf { long long cls = 0, team = 0, rounds = 0, iters = 0, t0 = 0, c0 = 0, c1 = 0, q0 = 0, q1 = 0, units = 0; };
 __device__ unsigned long long g_pf_units = 0, g_pf_units_max = 0, g_pf_open_cyc = 0, g_pf_unit_cyc = 0, g_pf_H = 0;
-#define BB_CLK() clock64()
+#define BB_PF(...) __VA_ARGS__
 #else
-#define BB_PROF_DECL
+struct BBProf {};
+#define BB_PF(...)
 #endif
 
 // resolve the hard items of this warp; returns, for a lane that passed hard = true, whether
 // its item (board it.b, pieces of `trio`) is solvable
-__device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uint32_t trio, const BBTables* T
-#ifdef BB_PROFILE
-                                              , long long& pf_rounds
-#endif
-                                              ) {
+__device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uint32_t trio, const BBTables* T,
+                                              BBProf& pf) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     bool solved = false;
@@ -91,9 +90,7 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
     const uint32_t nbr = BB_PLAN_NA(item.plan) + BB_PLAN_NB(item.plan);
     unsigned hmask = __ballot_sync(FULL, hard);
     while (hmask) {
-#ifdef BB_PROFILE
-        pf_rounds += 1;
-#endif
+        BB_PF(pf.rounds += 1;)
         const int H = __popc(hmask);
         const int ts = 32 / H;              // team size (>= 1)
         const int g = lane / ts;            // my team; teams >= H have no item
@@ -112,14 +109,9 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
         br.bb = 0; br.m0 = 0; br.m1 = 0; br.always = 0;
         br.A.pm = br.A.inb = br.A.offs = 0; br.A.meta = 0;
         br.B = br.A;
-#ifdef BB_PROFILE
-        const long long q0 = BB_CLK();
-#endif
+        BB_PF(pf.q0 = clock64();)
         if (in_team && t < BB_PLAN_NA(it.plan) + BB_PLAN_NB(it.plan)) bb_branch_open(br, it, T, tr, t);
-#ifdef BB_PROFILE
-        const long long q1 = BB_CLK();
-        unsigned long long nunits = 0;
-#endif
+        BB_PF(pf.q1 = clock64(); pf.units = 0;)
         // unit loop: every lane advances its branch by one second-level anchor, then a
         // ballot tells each team whether one of its lanes has proved the trio solvable
         unsigned found = 0;                 // bit l set: lane l found a solution
@@ -129,19 +121,15 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
             bool f = false;
             if (work) f = bb_branch_unit(br);
             found |= __ballot_sync(FULL, f);
-#ifdef BB_PROFILE
-            nunits += 1;
-#endif
+            BB_PF(pf.units += 1;)
         }
-#ifdef BB_PROFILE
-        if (lane == 0) {
-            atomicAdd(&g_pf_units, nunits);
-            atomicMax(&g_pf_units_max, nunits);
-            atomicAdd(&g_pf_open_cyc, (unsigned long long)(q1 - q0));
-            atomicAdd(&g_pf_unit_cyc, (unsigned long long)(BB_CLK() - q1));
+        BB_PF(if (lane == 0) {
+            atomicAdd(&g_pf_units, (unsigned long long)pf.units);
+            atomicMax(&g_pf_units_max, (unsigned long long)pf.units);
+            atomicAdd(&g_pf_open_cyc, (unsigned long long)(pf.q1 - pf.q0));
+            atomicAdd(&g_pf_unit_cyc, (unsigned long long)(clock64() - pf.q1));
             atomicAdd(&g_pf_H, (unsigned long long)H);
-        }
-#endif
+        })
         if (hard) {
             const int my = __popc(hmask & ((1u << lane) - 1u));          // index of the team working for me
             const unsigned tm = (ts == 32 ? FULL : ((1u << ts) - 1u)) << (my * ts);
@@ -156,20 +144,13 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
 
 __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, const BBTables* T,
                                                  uint64_t seed, uint64_t env_id, uint32_t& pieces,
-                                                 uint32_t& draw_ctr
-#ifdef BB_PROFILE
-                                                 , long long& pf_cls, long long& pf_team, long long& pf_rounds, long long& pf_iters
-#endif
-                                                 ) {
+                                                 uint32_t& draw_ctr, BBProf& pf) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     uint32_t attempts = 0;                  // candidates consumed by MY env so far
     unsigned pmask = __ballot_sync(FULL, pending);
     while (pmask) {
-#ifdef BB_PROFILE
-        const long long c0 = BB_CLK();
-        pf_iters += 1;
-#endif
+        BB_PF(pf.c0 = clock64(); pf.iters += 1;)
         // 1. groups of w lanes, one group per pending env; lane r classifies candidate ctr + r
         const int P = __popc(pmask);
         const int w = 32 / P;
@@ -197,18 +178,9 @@ __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, c
         const unsigned ga = (amask >> shift) & grp_bits;
         const int first_acc = ga ? (__ffs((int)ga) - 1) : w;
         const bool hard = cand && cls == BB_HARD && r < first_acc;
-#ifdef BB_PROFILE
-        const long long c1 = BB_CLK();
-        pf_cls += c1 - c0;
-#endif
-        const bool solved = bb_warp_solve(hard, item, trio, T
-#ifdef BB_PROFILE
-                                          , pf_rounds
-#endif
-                                          );
-#ifdef BB_PROFILE
-        pf_team += BB_CLK() - c1;
-#endif
+        BB_PF(pf.c1 = clock64(); pf.cls += pf.c1 - pf.c0;)
+        const bool solved = bb_warp_solve(hard, item, trio, T, pf);
+        BB_PF(pf.team += clock64() - pf.c1;)
         // 3. first solvable candidate of each group, in draw order
         const unsigned okmask = __ballot_sync(FULL, cand && (cls == BB_ACCEPT || solved));
         const unsigned go = (okmask >> shift) & grp_bits;
@@ -262,10 +234,8 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         o.mask[0] = o.mask[1] = o.mask[2] = 0;
     }
     const int steps = RANDOM ? n_steps : 1;
-    BB_PROF_DECL
-#ifdef BB_PROFILE
-    const long long pf_t0 = BB_CLK();
-#endif
+    BBProf pf;
+    BB_PF(pf.t0 = clock64();)
     for (int step = 0; step < steps; ++step) {
         BBMove mv;
         mv.ok = false; mv.needs_deal = false; mv.n = 0; mv.lines = 0; mv.gain = 0;
@@ -280,11 +250,7 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         }
         // all 32 lanes take part in the deal, with or without work of their own
         const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, E.seed, env_id,
-                                            s.pieces, s.draw_ctr
-#ifdef BB_PROFILE
-                                            , pf_cls, pf_team, pf_rounds, pf_iters
-#endif
-                                            );
+                                            s.pieces, s.draw_ctr, pf);
         if (live && mv.ok) {
             bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o);
             if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
@@ -334,21 +300,18 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         st_len = __reduce_add_sync(FULLM, (unsigned)st_len);
         const unsigned long long nlive = __popc(__ballot_sync(0xffffffffu, live));
         if ((threadIdx.x & 31) == 0) {
-#ifdef BB_PROFILE
-            const unsigned long long tot = (unsigned long long)(BB_CLK() - pf_t0);
-            atomicAdd(&stats[4], tot);
-            atomicMax(&stats[9], tot);
-            atomicMax(&stats[10], (unsigned long long)pf_rounds);
-            stats[11] = g_pf_units; stats[12] = g_pf_units_max; stats[13] = g_pf_open_cyc; stats[14] = g_pf_unit_cyc; stats[15] = g_pf_H;
-            // histogram of per-warp cycles in bins of 8192 cycles (stats[16..47])
-            atomicAdd(&stats[16 + (tot >> 13 > 31 ? 31 : tot >> 13)], 1ull);
-            // histogram of team rounds per warp (stats[48..63])
-            atomicAdd(&stats[48 + (pf_rounds > 15 ? 15 : pf_rounds)], 1ull);
-            atomicAdd(&stats[5], (unsigned long long)pf_cls);
-            atomicAdd(&stats[6], (unsigned long long)pf_team);
-            atomicAdd(&stats[7], (unsigned long long)pf_rounds);
-            atomicAdd(&stats[8], (unsigned long long)pf_iters);
-#endif
+            BB_PF(const unsigned long long tot = (unsigned long long)(clock64() - pf.t0);
+                  atomicAdd(&stats[4], tot);
+                  atomicAdd(&stats[5], (unsigned long long)pf.cls);
+                  atomicAdd(&stats[6], (unsigned long long)pf.team);
+                  atomicAdd(&stats[7], (unsigned long long)pf.rounds);
+                  atomicAdd(&stats[8], (unsigned long long)pf.iters);
+                  atomicMax(&stats[9], tot);
+                  atomicMax(&stats[10], (unsigned long long)pf.rounds);
+                  stats[11] = g_pf_units; stats[12] = g_pf_units_max; stats[13] = g_pf_open_cyc;
+                  stats[14] = g_pf_unit_cyc; stats[15] = g_pf_H;
+                  atomicAdd(&stats[16 + (tot >> 13 > 31 ? 31 : tot >> 13)], 1ull);           // cycles histogram
+                  atomicAdd(&stats[48 + (pf.rounds > 15 ? 15 : pf.rounds)], 1ull);)         // rounds histogram
             atomicAdd(&stats[0], nlive * (unsigned long long)n_steps);
             if (st_eps) {
                 atomicAdd(&stats[1], st_eps);
