@@ -94,6 +94,11 @@ class CVecEnv:
                        C.c_int(self.n_threads))
         return out
 
+    def set_board(self, k, board, pieces4):
+        """Overwrite env k's grid, trio and used bits (counters and stream cursor untouched)."""
+        pc = np.ascontiguousarray(pieces4, dtype=np.uint8)
+        lib().bbo_env_set_board(self._env(k), C.c_uint64(int(board)), _p(pc))
+
     def exhausted(self):
         L = lib()
         return any(L.bbo_env_exhausted(self._env(k)) for k in range(self.n))

@@ -314,3 +314,42 @@ def test_config4_size_and_tiny_sizes(torch):
     e = torch.zeros((0, 8), device="cuda")
     capi.gae(e, e, e, torch.zeros(8, device="cuda"), 0.99, 0.95, e, e, None)
     torch.cuda.synchronize()
+
+
+def test_hundred_candidate_exhaustion_on_gpu(torch):
+    """engine.py:171-172 through the speculative warp deal: envs that reject all 100 candidates
+    keep the last one; compared with the oracle (setup shared with tests/test_host_rules.py)."""
+    from bbgpu import capi
+    from oracle import bb_oracle_c as OC
+    from test_host_rules import _exhaustion_setup
+    n, seed = 40000, 31337
+    board, target, pieces, streams = _exhaustion_setup(n, seed)
+    ora = OC.CVecEnv(streams, n_threads=8)
+    for k in range(n):
+        ora.set_board(k, board, [0, 5, 9, 0b110])
+    h = capi.EnvHandle(n, seed)
+    st = h.get_state()
+    st["board"] = board
+    st["pieces"] = pieces
+    st["draw_ctr"] = 1
+    h.set_state(st)
+    B = _dev_buffers(torch, n)
+    acts = np.full(n, 1, np.int32)
+    oo = ora.step(acts)
+    go = _gpu_step(torch, h, B, acts)
+    draws = (go["info"] >> 11) & 0x7F
+    assert (draws == 100).sum() >= 20 and int(draws.max()) == 100
+    assert np.array_equal(oo["board"], go["board"]) and np.array_equal(oo["pieces"], _pieces4(go["pieces"]))
+    assert np.array_equal(oo["mask"], go["mask"]) and np.array_equal(oo["terminated"], go["terminated"])
+    assert np.array_equal(oo["rewards"].view(np.uint32), go["rewards"].view(np.uint32))
+    fresh = oo["terminated"] == 0
+    assert np.array_equal(ora.stats()[fresh, 7], h.get_state()["draw_ctr"][fresh])
+    # and one more ordinary step from there stays in lock step
+    m = oo["mask"]
+    bits = np.unpackbits(m.view(np.uint8).reshape(n, 24), axis=1, bitorder="little")
+    acts2 = (np.random.RandomState(0).rand(n, 192) * bits).argmax(1).astype(np.int32)
+    oo2 = ora.step(acts2)
+    go2 = _gpu_step(torch, h, B, acts2)
+    assert np.array_equal(oo2["board"], go2["board"]) and np.array_equal(oo2["mask"], go2["mask"])
+    assert np.array_equal(oo2["rewards"].view(np.uint32), go2["rewards"].view(np.uint32))
+    h.close()

@@ -173,3 +173,47 @@ def test_fused_random_policy_matches_oracle_with_host_policy_words():
         oo = ora.step(acts)
         assert np.array_equal(oo["board"], host.state["board"]), t
         assert np.array_equal(oo["rewards"].view(np.uint32), ho["rewards"].view(np.uint32)), t
+
+
+def _exhaustion_setup(n, seed):
+    """States whose third placement leaves a board on which only SINGLE fits: every row and column
+    has exactly one empty cell, no two of them adjacent (not even diagonally).  A candidate trio is
+    solvable only if it contains a SINGLE (8 % of draws), so a few envs in 10^5 reject all 100
+    candidates and keep the last one (engine.py:171-172)."""
+    empties = [(r, (3 * r) % 8) for r in range(8)]
+    target = (2 ** 64 - 1)
+    for r, c in empties:
+        target &= ~(1 << (r * 8 + c))
+    board = target & ~(1 << 1)                                   # cell (0,1) also empty: the SINGLE goes there
+    pieces = 0 | (5 << 8) | (9 << 16) | (0b110 << 24)            # trio (SINGLE, TRIO_H, TRIO_L1), pieces 1 and 2 used
+    from bbgpu import philox
+    L = 112
+    streams = np.zeros((n, L, 3), np.uint8)
+    streams[:, 1:] = philox.candidate_trios(seed, np.arange(n), L - 1, first_draw=1)   # cursor 1 <-> draw_ctr 1
+    return board, target, pieces, streams
+
+
+def test_hundred_candidate_exhaustion_host_vs_oracle():
+    n, seed = 40000, 31337
+    board, target, pieces, streams = _exhaustion_setup(n, seed)
+    ora = OC.CVecEnv(streams, n_threads=8)
+    host = H.HostEnv(n, seed)
+    for k in range(n):
+        ora.set_board(k, board, [0, 5, 9, 0b110])
+    host.state["board"] = board
+    host.state["pieces"] = pieces
+    host.state["draw_ctr"] = 1
+    acts = np.full(n, 1, np.int32)                               # piece 0 (SINGLE) at row 0, col 1
+    oo, ho = ora.step(acts), host.step(acts)
+    draws = (ho["info"] >> 11) & 0x7F
+    assert (draws == 100).sum() >= 1, "no env exhausted its 100 candidates: enlarge n"
+    assert np.array_equal(oo["board"], host.state["board"]) and np.array_equal(oo["pieces"], host.pieces4())
+    assert np.array_equal(oo["mask"], ho["mask"]) and np.array_equal(oo["terminated"], ho["terminated"])
+    assert np.array_equal(oo["rewards"].view(np.uint32), ho["rewards"].view(np.uint32))
+    # draws consumed: oracle counts its constructor draw too
+    fresh = oo["terminated"] == 0
+    assert np.array_equal(ora.stats()[fresh, 7], host.state["draw_ctr"][fresh])
+    # both outcomes of an exhausted deal occur: game over (nothing of the kept trio fits) and
+    # play continues (the kept, unsolvable trio still contains a piece that fits: engine.py:440-441)
+    ex = draws == 100
+    assert ex.sum() >= 20 and oo["terminated"][ex].any() and not oo["terminated"][ex].all()
