@@ -260,7 +260,14 @@ def kernel_rooflines(dev, peak):
     b = 420 * n
     out["K3_masked_sample_bf16"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
                                     "frac_of_hbm_peak": b / t / 1e9 / peak}
-    del logits, lb
+    # K3 backward (PPO update path): 768 B logits read + 768 B grad written + 36 B mask/action/grads per row
+    gl = torch.empty_like(logits)
+    g1, g2 = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    t = timeit(lambda: capi.masked_head_backward(logits, mask, n, act, g1, g2, gl))
+    b = (768 * 2 + 36) * n
+    out["K3_backward_f32"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                              "frac_of_hbm_peak": b / t / 1e9 / peak}
+    del logits, lb, gl
     # K2 obs unpack: 36 B in, 1,024 B f32 planes out (+ 192 B u8 mask) per env
     board = torch.randint(-2 ** 62, 2 ** 62, (n,), dtype=torch.int64, device=dev)
     pieces = torch.randint(0, 37, (n,), dtype=torch.int32, device=dev) * 0x010101
@@ -505,6 +512,14 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * Ke / float(te.item())
+    # same loop, but the caller touches the dense reference-layout observation every step
+    # (board (N,8,8) f32, pieces (N,3,8,8) f32, action_mask (N,192) int8 expanded on the host)
+    Kd = min(Ke, 5)
+    t0 = time.perf_counter()
+    for _ in range(Kd):
+        obs, rew, term, trunc, infos = venv.step(venv.sample_valid_actions())
+        _ = obs["board"], obs["pieces"], obs["action_mask"]
+    e2e_dense = n * Kd / (time.perf_counter() - t0)
     h2d = 4 * n
     d2h = 4 * n + (4 + 1 + 8 + 4 + 24 + 4 + 4) * n
 
@@ -545,7 +560,7 @@ def main():
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
                          "launch_us": per_launch_s * 1e6},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "VectorizedBlockBlastEnv(output='numpy', reuse_buffers=True): sample_valid_actions() + "
+                    "steps": Ke, "dense_obs_materialised_env_steps_per_sec_rank0": e2e_dense, "api": "VectorizedBlockBlastEnv(output='numpy', reuse_buffers=True): sample_valid_actions() + "
                                         "step(actions); numpy results are zero-copy views of double-buffered pinned memory, "
                                         "packed obs expanded lazily on host"},
             "clocks": clocks,

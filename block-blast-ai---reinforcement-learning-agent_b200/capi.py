@@ -23,6 +23,10 @@ REWARD_DEFAULTS = dict(line_clear_base=1.0, block_placed=0.01, game_over_penalty
                        hole_penalty=-0.05, center_bonus=0.02, combo_multiplier_bonus=0.5,
                        survival_bonus=0.001)   # reference block_blast_env.py:63-71
 
+#: 32-byte record of bb_env_set_episode_end_buffer
+EPISODE_END_DTYPE = np.dtype([("board", "<u8"), ("pieces", "<u4"), ("lines_total", "<i4"), ("max_streak", "<i4"),
+                              ("blocks_total", "<i4"), ("holes_fill", "<u4"), ("last_move", "<u4")])
+
 #: 48-byte per-env record of bb_env_get_state / bb_env_set_state
 STATE_DTYPE = np.dtype([("board", "<u8"), ("pieces", "<u4"), ("aux", "<u4"), ("score", "<i4"),
                         ("streak", "<i4"), ("moves", "<i4"), ("lines_total", "<i4"),
@@ -54,6 +58,7 @@ def lib():
     L.bb_env_destroy.argtypes = [vp]
     L.bb_env_num_envs.argtypes = [vp]
     L.bb_env_num_envs.restype = i64
+    L.bb_env_set_episode_end_buffer.argtypes = [vp, vp]
     L.bb_env_reset.argtypes = [vp, vp, vp, vp]
     L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
@@ -62,7 +67,7 @@ def lib():
     L.bb_env_sample_valid_actions.argtypes = [vp, u64, vp, vp, vp]
     L.bb_env_get_state.argtypes = [vp, vp, vp]
     L.bb_env_set_state.argtypes = [vp, vp, vp]
-    L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
     L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
     L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
@@ -133,6 +138,11 @@ class EnvHandle:
         except Exception:
             pass
 
+    def set_episode_end_buffer(self, records):
+        """records: CUDA uint8 tensor of n*32 bytes (or None); must outlive the handle's use of it."""
+        self._ep_end_keepalive = records
+        check(lib().bb_env_set_episode_end_buffer(self.h, ptr(records)))
+
     def reset(self, reset_mask=None, mask_out=None):
         check(lib().bb_env_reset(self.h, ptr(reset_mask), ptr(mask_out), current_stream()))
 
@@ -166,9 +176,10 @@ class EnvHandle:
         assert rec.shape == (self.n,)
         check(lib().bb_env_set_state(self.h, ptr(rec), current_stream()))
 
-    def step_host(self, actions, rewards, terminated, board=None, pieces=None, mask=None, ep_score=None, ep_len=None):
+    def step_host(self, actions, rewards, terminated, board=None, pieces=None, mask=None, ep_score=None, ep_len=None,
+                  info=None):
         check(lib().bb_env_step_host(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(board), ptr(pieces),
-                                     ptr(mask), ptr(ep_score), ptr(ep_len), current_stream()))
+                                     ptr(mask), ptr(ep_score), ptr(ep_len), ptr(info), current_stream()))
 
 
 def unpack_obs(board, pieces, mask, mask_stride, obs=None, mask_dense=None, n=None):

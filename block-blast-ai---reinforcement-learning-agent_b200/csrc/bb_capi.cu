@@ -30,6 +30,7 @@ struct bb_env {
     uint64_t* d_mask;
     int32_t* d_ep_score;
     int32_t* d_ep_len;
+    uint32_t* d_info;
 };
 
 static const double BB_DEFAULT_CFG[7] = {1.0, 0.01, -1.0, -0.05, 0.02, 0.5, 0.001};
@@ -93,12 +94,18 @@ int bb_env_destroy(bb_env* e) {
     if (!e) return 0;
     cudaFree(e->arr.s0); cudaFree(e->arr.s1); cudaFree(e->arr.s2);
     cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_terminated); cudaFree(e->d_board);
-    cudaFree(e->d_pieces); cudaFree(e->d_mask); cudaFree(e->d_ep_score); cudaFree(e->d_ep_len);
+    cudaFree(e->d_pieces); cudaFree(e->d_mask); cudaFree(e->d_ep_score); cudaFree(e->d_ep_len); cudaFree(e->d_info);
     delete e;
     return 0;
 }
 
 int64_t bb_env_num_envs(const bb_env* e) { return e ? e->arr.n : -1; }
+
+int bb_env_set_episode_end_buffer(bb_env* e, void* records) {
+    if (!e) return fail(-1, "bb_env_set_episode_end_buffer: env is NULL");
+    e->arr.ep_end = (BBEpisodeEnd*)records;
+    return 0;
+}
 
 int bb_env_reset(bb_env* e, const uint8_t* reset_mask, uint64_t* mask_out, void* stream) {
     if (!e) return fail(-1, "bb_env_reset: env is NULL");
@@ -208,6 +215,7 @@ static int ensure_staging(bb_env* e) {
     if (err == cudaSuccess) err = cudaMalloc(&e->d_mask, 3 * n * sizeof(uint64_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->d_ep_score, n * sizeof(int32_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->d_ep_len, n * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_info, n * sizeof(uint32_t));
     if (err != cudaSuccess) return fail(-2, "bb_env_step_host: cudaMalloc staging", err);
     cudaMemset(e->d_ep_score, 0, n * sizeof(int32_t));
     cudaMemset(e->d_ep_len, 0, n * sizeof(int32_t));
@@ -216,7 +224,7 @@ static int ensure_staging(bb_env* e) {
 
 int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint8_t* h_terminated,
                      uint64_t* h_board, uint32_t* h_pieces, uint64_t* h_mask, int32_t* h_ep_score,
-                     int32_t* h_ep_len, void* stream) {
+                     int32_t* h_ep_len, uint32_t* h_info, void* stream) {
     if (!e) return fail(-1, "bb_env_step_host: env is NULL");
     if (!h_actions || !h_rewards || !h_terminated) return fail(-1, "bb_env_step_host: actions/rewards/terminated are required");
     if (int rc = ensure_staging(e)) return rc;
@@ -224,7 +232,8 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
     cudaStream_t s = (cudaStream_t)stream;
     BB_CUDA(cudaMemcpyAsync(e->d_actions, h_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s), "H2D actions");
     BB_CUDA(bb_launch_step(e->arr, e->cfg, e->d_actions, e->d_rewards, e->d_terminated, h_mask ? e->d_mask : nullptr,
-                           h_ep_score ? e->d_ep_score : nullptr, h_ep_len ? e->d_ep_len : nullptr, nullptr, s),
+                           h_ep_score ? e->d_ep_score : nullptr, h_ep_len ? e->d_ep_len : nullptr,
+                           h_info ? e->d_info : nullptr, s),
             "bb_env_step_host launch");
     if (h_board || h_pieces)
         BB_CUDA(bb_launch_observe(e->arr, h_board ? e->d_board : nullptr, h_pieces ? e->d_pieces : nullptr, nullptr, s),
@@ -236,6 +245,7 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
     if (h_mask) BB_CUDA(cudaMemcpyAsync(h_mask, e->d_mask, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s), "D2H mask");
     if (h_ep_score) BB_CUDA(cudaMemcpyAsync(h_ep_score, e->d_ep_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_score");
     if (h_ep_len) BB_CUDA(cudaMemcpyAsync(h_ep_len, e->d_ep_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_len");
+    if (h_info) BB_CUDA(cudaMemcpyAsync(h_info, e->d_info, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H info");
     BB_CUDA(cudaStreamSynchronize(s), "bb_env_step_host sync");
     return 0;
 }

@@ -276,7 +276,7 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, E.seed, env_id,
                                             s.pieces, s.draw_ctr, pf);
         if (live && mv.ok) {
-            bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o);
+            bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o, E.ep_end ? E.ep_end + i : nullptr);
             if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
         }
         if (RANDOM && per_step && live) {

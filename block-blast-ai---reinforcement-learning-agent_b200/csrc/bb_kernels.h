@@ -20,6 +20,7 @@ struct BBEnvArrays {
     int64_t env_offset;   // global id of env 0 of this shard
     uint64_t seed;
     uint32_t flags;
+    BBEpisodeEnd* ep_end;   // optional [n] records written where an env terminates (bb_env_set_episode_end_buffer)
 };
 
 cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const int32_t* actions,

@@ -570,13 +570,23 @@ BB_HD void bb_action_mask(const BBState& s, const BBTables* T, uint64_t m[3]) {
 struct BBStepOut {
     float reward;
     uint32_t terminated;   // 0/1
-    uint32_t info;         // bit0 invalid, bits1-3 lines, bits4-7 blocks, bits8-10 combo mult, bits11-17 draws
+    uint32_t info;         // bit0 invalid, bits1-3 lines, 4-7 blocks, 8-10 combo mult, 11-17 draws, 18-31 score gained
     int32_t gain;          // score gained by this move
     int32_t ep_score, ep_len;   // valid when terminated
     uint64_t mask[3];      // action mask of the state after the step (after auto-reset)
 };
 
 struct BBMove { int n, lines, gain; bool ok, needs_deal; };
+
+// Written only when an env terminates: what the reference keeps in infos[i] for a finished
+// episode (block_blast_env.py:266-288 + terminal_observation, wrappers.py:97-100).  32 bytes.
+struct BBEpisodeEnd {
+    uint64_t board;            // terminal board
+    uint32_t pieces;           // terminal trio + used bits
+    int32_t lines_total, max_streak, blocks_total;
+    uint32_t holes_fill;       // holes | filled cells << 8
+    uint32_t last_move;        // the info word of the terminal move
+};
 
 // First half of a step: decode + validate (block_blast_env.py:104-118, :240-245,
 // engine.py:326-346), place, clear, streak and score (engine.py:405-429).  On an invalid
@@ -628,7 +638,7 @@ BB_HD BBMove bb_env_pre(BBState& s, int action, const BBTables* T, BBStepOut& o)
 // (engine.py:440-441) — the same three valid masks are the next observation's action mask —
 // then the shaped reward, and the vec-env's auto-reset (wrappers.py:96-102).
 BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTables* T, const BBRewardCfg& cfg,
-                       uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o) {
+                       uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o, BBEpisodeEnd* ep_end = nullptr) {
     bb_action_mask(s, T, o.mask);
     const bool over = (o.mask[0] | o.mask[1] | o.mask[2]) == 0ull;
     const int h = bb_holes(s.board), ctr = bb_center(s.board);
@@ -636,11 +646,19 @@ BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTab
     s.aux = (uint32_t)h | ((uint32_t)ctr << 8) | ((over ? 1u : 0u) << 16);
     o.terminated = over ? 1u : 0u;
     o.gain = mv.gain;
+    // score gained <= 9 + 6*80*4*8 = 15,369 fits the 14 spare bits
     o.info = ((uint32_t)mv.lines << 1) | ((uint32_t)mv.n << 4) |
-             ((uint32_t)(mv.lines > 0 ? (mv.lines < 4 ? mv.lines : 4) : 1) << 8) | (draws << 11);
+             ((uint32_t)(mv.lines > 0 ? (mv.lines < 4 ? mv.lines : 4) : 1) << 8) | (draws << 11) |
+             ((uint32_t)mv.gain << 18);
     if (over) {
         o.ep_score = s.score;
         o.ep_len = s.moves;
+        if (ep_end) {
+            ep_end->board = s.board; ep_end->pieces = s.pieces;
+            ep_end->lines_total = s.lines_total; ep_end->max_streak = s.max_streak; ep_end->blocks_total = s.blocks_total;
+            ep_end->holes_fill = (uint32_t)h | ((uint32_t)bb_popc(s.board) << 8);
+            ep_end->last_move = o.info;
+        }
         if (!(flags & BB_FLAG_NO_AUTO_RESET)) {
             bb_reset_state(s, seed, env_id, flags);
             // empty board, nothing used: every in-bounds anchor is valid

@@ -125,6 +125,12 @@ class LazyObs(dict):
         return k in ("board", "pieces", "action_mask")
 
 
+def _last_move(word):
+    """info word -> the reference's info['last_move'] (block_blast_env.py:281-286)."""
+    return {"blocks_placed": (word >> 4) & 0xF, "lines_cleared": (word >> 1) & 7,
+            "combo_multiplier": (word >> 8) & 7, "score_gained": (word >> 18) & 0x3FFF}
+
+
 class LazyInfos:
     """Sequence of per-env info dicts (block_blast_env.py:266-288) built on demand.
 
@@ -136,6 +142,16 @@ class LazyInfos:
         self._venv, self._term, self._inv = venv, terminated, invalid
         self._eps, self._epl = ep_score, ep_len
         self._state = None
+        self._ends = None
+        self._step_id = getattr(venv, "_step_id", 0)
+
+    def _end(self, i):
+        """Episode-end record of env i (terminal state), fetched from the device on first use."""
+        if self._ends is None:
+            if self._step_id != getattr(self._venv, "_step_id", 0):
+                raise RuntimeError("infos of an older step: the episode-end log has been overwritten")
+            self._ends = self._venv._d_ep_end.cpu().numpy().view(capi.EPISODE_END_DTYPE).copy()
+        return self._ends[i]
 
     def __len__(self):
         return len(self._term)
@@ -151,15 +167,25 @@ class LazyInfos:
         if i < 0:
             i += len(self)
         if bool(self._term[i]):
-            # stats of the finished episode; the env has already been reset
+            # the finished episode (the env itself has already been reset): wrappers.py:97-100
+            e = self._end(i)
             return {"score": int(self._eps[i]), "final_score": int(self._eps[i]), "moves": int(self._epl[i]),
-                    "invalid_action": False}
+                    "lines_cleared": int(e["lines_total"]), "max_combo": int(e["max_streak"]),
+                    "blocks_placed": int(e["blocks_total"]), "board_fill": (int(e["holes_fill"]) >> 8) / 64,
+                    "holes": int(e["holes_fill"]) & 0xFF, "invalid_action": False,
+                    "last_move": _last_move(int(e["last_move"])),
+                    "terminal_observation": {"board": expand_board(np.array([e["board"]], np.uint64))[0],
+                                             "pieces": expand_pieces(np.array([e["pieces"]], np.uint32))[0],
+                                             "action_mask": np.zeros(ACTION_SPACE_SIZE, np.int8)}}
         s = self._rec()[i]
         board = int(s["board"])
-        return {"score": int(s["score"]), "moves": int(s["moves"]), "lines_cleared": int(s["lines_total"]),
-                "max_combo": int(s["max_streak"]), "blocks_placed": int(s["blocks_total"]),
-                "board_fill": bin(board).count("1") / 64, "holes": int(s["aux"] & 0xFF),
-                "invalid_action": bool(self._inv[i]) if self._inv is not None else False}
+        word = int(self._inv[i]) if self._inv is not None else 0          # the step's info word
+        d = {"score": int(s["score"]), "moves": int(s["moves"]), "lines_cleared": int(s["lines_total"]),
+             "max_combo": int(s["max_streak"]), "blocks_placed": int(s["blocks_total"]),
+             "board_fill": bin(board).count("1") / 64, "holes": int(s["aux"] & 0xFF), "invalid_action": bool(word & 1)}
+        if self._inv is not None and not (word & 1):
+            d["last_move"] = _last_move(word)
+        return d
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -203,6 +229,9 @@ class VectorizedBlockBlastEnv:
         self._d_ep_score = torch.zeros(n, dtype=torch.int32, device=dev)
         self._d_ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self._d_info = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._d_ep_end = torch.zeros(n * 32, dtype=torch.uint8, device=dev)      # episode-end log (32 B records)
+        self._handle.set_episode_end_buffer(self._d_ep_end)
+        self._step_id = 0
         if output == "numpy":
             pin = dict(pin_memory=True)
             self._h_actions = torch.zeros(n, dtype=torch.int32, **pin)
@@ -212,7 +241,8 @@ class VectorizedBlockBlastEnv:
                                  pieces=torch.zeros(n, dtype=torch.int32, **pin),
                                  mask=torch.zeros((3, n), dtype=torch.int64, **pin),
                                  ep_score=torch.zeros(n, dtype=torch.int32, **pin),
-                                 ep_len=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
+                                 ep_len=torch.zeros(n, dtype=torch.int32, **pin),
+                                 info=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
             self._h_flip = 0
         self._dones = np.zeros(n, dtype=bool)
         self._h_actions_np = self._h_actions.numpy() if output == "numpy" else None
@@ -256,6 +286,7 @@ class VectorizedBlockBlastEnv:
             self._handle.close()
             self.seed = int(seed)
             self._make_handle()     # deals once, like constructing the reference envs
+            self._handle.set_episode_end_buffer(self._d_ep_end)
         self._handle.reset()
         self._dones.fill(False)
         obs = self._obs_numpy() if self.output == "numpy" else self._obs_device()
@@ -265,6 +296,7 @@ class VectorizedBlockBlastEnv:
         """wrappers.py:75-116: returns (obs, rewards, terminated, truncated, infos)."""
         torch = self._torch
         n = self.num_envs
+        self._step_id += 1
         if self.output == "numpy":
             a = np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions).reshape(-1)
             assert a.shape[0] == n, "expected %d actions" % n
@@ -273,13 +305,14 @@ class VectorizedBlockBlastEnv:
             self._h_flip ^= 1
             h = self._h_sets[self._h_flip]
             self._handle.step_host(self._h_actions, h["rewards"], h["term"], h["board"], h["pieces"], h["mask"],
-                                   h["ep_score"], h["ep_len"])
+                                   h["ep_score"], h["ep_len"], h["info"])
             keep = (lambda x: x) if self.reuse_buffers else (lambda x: x.copy())
             rewards = keep(h["rewards"].numpy())
             term = h["term"].numpy().view(bool) if self.reuse_buffers else h["term"].numpy().astype(bool)
             obs = LazyObs(keep(h["board"].numpy().view(np.uint64)), keep(h["pieces"].numpy().view(np.uint32)),
                           keep(h["mask"].numpy().view(np.uint64)))
-            infos = LazyInfos(self, term, None, keep(h["ep_score"].numpy()), keep(h["ep_len"].numpy()))
+            infos = LazyInfos(self, term, keep(h["info"].numpy().view(np.uint32)), keep(h["ep_score"].numpy()),
+                              keep(h["ep_len"].numpy()))
             return obs, rewards, term, np.zeros(n, dtype=bool), infos
         if isinstance(actions, torch.Tensor):
             self._d_actions.copy_(actions.reshape(-1), non_blocking=True)
@@ -373,8 +406,7 @@ class BlockBlastEnv:
                 "board_fill": bin(int(s["board"])).count("1") / 64, "holes": _holes(int(s["board"])),
                 "invalid_action": False}
         if info_word is not None:
-            info["last_move"] = {"blocks_placed": (info_word >> 4) & 0xF, "lines_cleared": (info_word >> 1) & 7,
-                                 "combo_multiplier": (info_word >> 8) & 7}
+            info["last_move"] = _last_move(info_word)
         return info
 
     def reset(self, seed=None, options=None):
@@ -388,7 +420,7 @@ class BlockBlastEnv:
     def step(self, action):
         self._a.fill_(int(action))
         self._h.step(self._a, self._r, self._t, None, None, None, self._i)
-        word = int(self._i.item())
+        word = int(self._i.item()) & 0xFFFFFFFF
         reward = float(self._r.item())
         terminated = bool(self._t.item())
         if word & 1:

@@ -64,6 +64,15 @@ int bb_env_create(bb_env** out, int64_t n_envs, uint64_t seed, int64_t global_en
 int bb_env_destroy(bb_env* env);
 int64_t bb_env_num_envs(const bb_env* env);
 
+/* Optional episode-end log: `records` is a device array of n_envs 32-byte records
+ *   {u64 board; u32 pieces; i32 lines_total, max_streak, blocks_total; u32 holes | filled<<8;
+ *    u32 last_move (the info word of the terminal move)}
+ * Record i is written by every later step call in which env i terminates, with the TERMINAL
+ * state (before the auto-reset): what the reference leaves in infos[i] for a finished episode
+ * (block_blast_env.py:266-288, wrappers.py:97-100).  The pointer is retained until replaced;
+ * NULL switches the log off.  This is the only pointer the library keeps between calls. */
+int bb_env_set_episode_end_buffer(bb_env* env, void* records);
+
 /* VectorizedBlockBlastEnv.reset (wrappers.py:53-73).  reset_mask: device u8[n] or NULL (= all).
  * mask_out: device u64[3*n] or NULL. */
 int bb_env_reset(bb_env* env, const uint8_t* reset_mask, uint64_t* mask_out, void* stream);
@@ -81,7 +90,7 @@ int bb_env_reset(bb_env* env, const uint8_t* reset_mask, uint64_t* mask_out, voi
  *   ep_len      device i32[n]     written only where terminated: info['moves']       (NULL ok)
  *   info_out    device u32[n]     bit0 invalid_action, bits1-3 lines_cleared, bits4-7
  *                                 blocks_placed, bits8-10 combo_multiplier, bits11-17 candidate
- *                                 trios drawn                                    (NULL ok)
+ *                                 trios drawn, bits18-31 score_gained           (NULL ok)
  */
 int bb_env_step(bb_env* env, const int32_t* actions, float* rewards, uint8_t* terminated,
                 uint64_t* mask_out, int32_t* ep_score, int32_t* ep_len, uint32_t* info_out,
@@ -129,10 +138,11 @@ int bb_env_set_state(bb_env* env, const void* host_records, void* stream);
 /* Same as bb_env_step but with HOST buffers (pinned memory recommended): copies actions to
  * the device, steps, copies rewards/terminated/packed obs back, synchronises.  This is the
  * call the numpy-facing VectorizedBlockBlastEnv.step makes.  board/pieces/mask/ep_* may be
- * NULL to skip that copy. */
+ * NULL to skip that copy; h_info receives the per-env info word of bb_env_step. */
 int bb_env_step_host(bb_env* env, const int32_t* h_actions, float* h_rewards,
                      uint8_t* h_terminated, uint64_t* h_board, uint32_t* h_pieces,
-                     uint64_t* h_mask, int32_t* h_ep_score, int32_t* h_ep_len, void* stream);
+                     uint64_t* h_mask, int32_t* h_ep_score, int32_t* h_ep_len, uint32_t* h_info,
+                     void* stream);
 
 /* Observation expansion (engine.get_observation + Piece.to_mask, engine.py:489-507,
  * src/game/pieces.py:39-45; network input cat([board, pieces]), src/models/network.py:152-158).

@@ -196,7 +196,9 @@ def test_state_roundtrip_and_host_step_equals_device_step(torch):
     ha, hr, ht = pin(torch.int32), pin(torch.float32), pin(torch.uint8)
     hb, hp, hm, hs, hl = pin(torch.int64), pin(torch.int32), pin(torch.int64, (3, n)), pin(torch.int32), pin(torch.int32)
     ha.numpy()[:] = acts
-    b.step_host(ha, hr, ht, hb, hp, hm, hs, hl)
+    hi_ = pin(torch.int32)
+    b.step_host(ha, hr, ht, hb, hp, hm, hs, hl, hi_)
+    assert np.array_equal(hi_.numpy().view(np.uint32), go["info"])
     assert np.array_equal(hr.numpy().view(np.uint32), go["rewards"].view(np.uint32))
     assert np.array_equal(ht.numpy(), go["terminated"])
     assert np.array_equal(hb.numpy().view(np.uint64), go["board"])

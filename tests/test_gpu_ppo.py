@@ -221,3 +221,45 @@ def test_batched_deterministic_evaluation(torch):
     assert r1["finished"] == 200 and np.array_equal(r1["scores"], r2["scores"]) and np.array_equal(r1["lengths"], r2["lengths"])
     assert 3 < r1["mean_length"] < 60 and r1["min_score"] > 0 and r1["max_score"] >= r1["mean_score"]
     assert agent.training            # mode restored
+
+
+def test_vectorized_env_infos_match_oracle_including_terminal_observation(torch):
+    """infos[i] of every step (block_blast_env.py:266-288) and, for finished episodes, the
+    terminal statistics, final_score and terminal_observation (wrappers.py:97-100), against the
+    Python oracle fed the same Philox trio streams."""
+    from bbgpu import philox
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    from oracle import bb_oracle as O
+    n, seed, T = 16, 77, 260
+    streams = philox.candidate_trios(seed, np.arange(n), 600)
+
+    def mk(i):
+        it = iter(streams[i])
+        return O.Env(draw=lambda: next(it))
+    ora = O.VecEnv([mk(i) for i in range(n)])          # each oracle env dealt draw 0 in its constructor
+    venv = VectorizedBlockBlastEnv(n, seed=seed)        # ... like bb_env_create; no further reset on either side
+    rs = np.random.RandomState(4)
+    n_term = 0
+    for t in range(T):
+        masks = venv.get_action_masks()
+        acts = np.array([int(rs.choice(np.where(masks[i])[0])) if rs.rand() > 0.05 else int(rs.randint(0, 192)) for i in range(n)])
+        oobs, orew, oterm, _, oinfos = ora.step(acts)
+        gobs, grew, gterm, gtrunc, ginfos = venv.step(acts)
+        assert np.array_equal(orew.view(np.uint32), grew.view(np.uint32)) and np.array_equal(oterm, gterm)
+        for i in range(n):
+            oi, gi = oinfos[i], ginfos[i]
+            for k in ("score", "moves", "lines_cleared", "max_combo", "blocks_placed", "holes", "invalid_action"):
+                assert oi[k] == gi[k], (t, i, k, oi[k], gi[k])
+            assert abs(oi["board_fill"] - gi["board_fill"]) < 1e-12
+            assert ("last_move" in oi) == ("last_move" in gi), (t, i)
+            if "last_move" in oi:
+                assert oi["last_move"] == gi["last_move"], (t, i, oi["last_move"], gi["last_move"])
+            if oterm[i]:
+                n_term += 1
+                assert gi["final_score"] == oi["final_score"]
+                for k in ("board", "pieces", "action_mask"):
+                    assert np.array_equal(oi["terminal_observation"][k], gi["terminal_observation"][k]), (t, i, k)
+            else:
+                assert "final_score" not in gi
+    assert n_term > 100
+    venv.close()
