@@ -98,27 +98,21 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
     unsigned hmask = __ballot_sync(FULL, hard);
     while (hmask) {
         BB_PF(pf.rounds += 1;)
-        // owner side: inclusive prefix of the remaining branch counts
+        // Walk the hard lanes in order (a handful per round): their remaining branch counts laid
+        // end to end are the round's work list, worker lane L serves entry L.  The shuffles of
+        // this loop are independent of each other, unlike a prefix scan + binary search.
         const int rem = hard ? (int)(nbr - next) : 0;
-        int incl = rem;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += o;
+        int excl = 32;                       // owner side: where MY item's branches start (32 = not served)
+        int owner = lane, o_excl = 0, o_rem = 0;
+        bool in_team = false;
+        int run = 0;
+        for (unsigned m = hmask; m && run < 32; m &= m - 1u) {
+            const int h = __ffs((int)m) - 1;
+            const int r = __shfl_sync(FULL, rem, h);
+            if (lane == h) excl = run;
+            if (lane >= run && lane < run + r) { owner = h; o_excl = run; o_rem = r; in_team = true; }
+            run += r;
         }
-        const int excl = incl - rem;
-        const int total = __shfl_sync(FULL, incl, 31);
-        // worker side: lane L serves global branch number L; find its owner = first lane with incl > L
-        int lo = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int probe = __shfl_sync(FULL, incl, lo + step - 1);
-            if (probe <= lane) lo += step;
-        }
-        const bool in_team = lane < total;
-        const int owner = in_team ? lo : lane;
-        const int o_excl = __shfl_sync(FULL, excl, owner);
-        const int o_rem = __shfl_sync(FULL, rem, owner);
         const int served_o = min(o_rem, 32 - o_excl);               // lanes working on my owner's item this round
         const unsigned team_mask = in_team ? ((served_o >= 32 ? FULL : ((1u << served_o) - 1u)) << o_excl) : 0u;
         BBItem it;

@@ -35,8 +35,8 @@
 struct BBTables {
     uint64_t mask[BB_TABLE_N];   // piece cells at the origin (slots 37..39 are zero padding)
     uint64_t inb[BB_TABLE_N];    // anchors whose bounding box stays on the board
-    uint64_t offs[BB_TABLE_N];   // cell offsets, 6 bits each: bits 0..29 = #0..4, bits 32..55 = #5..8
-    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
+    uint64_t offs[BB_TABLE_N];   // cell offsets #0..7, one byte each
+    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16 | cell offset #8 << 24
 };
 
 #define BB_META_N(m) ((m) & 0xFu)
@@ -73,6 +73,13 @@ BB_HD int bb_popc(uint64_t x) {
     return __popcll(x);
 #else
     return __builtin_popcountll(x);
+#endif
+}
+BB_HD int bb_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
 #endif
 }
 BB_HD int bb_ctz(uint64_t x) {   // x != 0
@@ -130,48 +137,70 @@ BB_HD uint64_t bb_shr(uint64_t e, uint32_t o) {
 #endif
 }
 
+// byte k (0..3) of a 32-bit word, zero-extended: one PRMT on the device
+BB_HD uint32_t bb_byte(uint32_t w, int k) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + (uint32_t)k);
+#else
+    return (w >> (8 * k)) & 0xFFu;
+#endif
+}
+
 // All anchors at which piece p fits on the EMPTY-cell set e = ~board: board.py:71-93 for the
-// 64 anchors at once, one shift-AND per cell of the piece.  The offset list is padded with
-// repeats, so the first four steps need no predicate (31 of 37 pieces have <= 4 cells).
+// 64 anchors at once, one shift-AND per cell of the piece.  The offset list (a byte per cell,
+// the ninth in the meta word) is padded with repeats, so the first four steps need no predicate
+// (31 of 37 pieces have <= 4 cells).
 BB_HD uint64_t bb_valid(uint64_t e, const BBPiece& p) {
     const uint32_t lo = (uint32_t)p.offs, hi = (uint32_t)(p.offs >> 32);
-    uint64_t v = p.inb & bb_shr(e, lo & 63u) & bb_shr(e, (lo >> 6) & 63u);
-    v &= bb_shr(e, (lo >> 12) & 63u) & bb_shr(e, (lo >> 18) & 63u);
+    uint64_t v = p.inb & bb_shr(e, bb_byte(lo, 0)) & bb_shr(e, bb_byte(lo, 1));
+    v &= bb_shr(e, bb_byte(lo, 2)) & bb_shr(e, lo >> 24);
     const uint32_t n = BB_META_N(p.meta);
     if (n > 4) {
-        v &= bb_shr(e, (lo >> 24) & 63u) & bb_shr(e, hi & 63u);
+        v &= bb_shr(e, bb_byte(hi, 0)) & bb_shr(e, bb_byte(hi, 1));
         if (n > 6) {
-            v &= bb_shr(e, (hi >> 6) & 63u) & bb_shr(e, (hi >> 12) & 63u);
-            v &= bb_shr(e, (hi >> 18) & 63u);
+            v &= bb_shr(e, bb_byte(hi, 2)) & bb_shr(e, hi >> 24);
+            v &= bb_shr(e, p.meta >> 24);
         }
     }
     return v;
 }
 
+// Rows of a 32-bit half board (one byte per row).  A byte is 0xFF iff adding 1 to its low seven
+// bits carries into bit 7 while bit 7 is set; the sum cannot carry into the next byte.
+// bb_rowflags32: bit 7 of byte r = row r full (other bits unspecified);
+// bb_rowmask32: 0xFF in every full row's byte, 0 elsewhere (sign-replicating PRMT on the device).
+BB_HD uint32_t bb_rowflags32(uint32_t x) { return ((x & 0x7F7F7F7Fu) + 0x01010101u) & x; }
+BB_HD uint32_t bb_rowmask32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t m;   // selector nibbles 8..B: replicate the sign bit of byte 0..3 (__byte_perm cannot)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(bb_rowflags32(x)), "r"(0u), "r"(0xBA98u));
+    return m;
+#else
+    return ((bb_rowflags32(x) & 0x80808080u) >> 7) * 0xFFu;
+#endif
+}
+// bit c set iff column c is full
+BB_HD uint32_t bb_fullcols(uint32_t lo, uint32_t hi) {
+    uint32_t c = lo & hi;
+    c &= c >> 16;
+    c &= c >> 8;
+    return c & 0xFFu;
+}
+
 // Full rows / columns are detected on the same board, then all removed (board.py:166-193).
 // Returns the cleared board; *lines = rows + cols.
 BB_HD uint64_t bb_clear(uint64_t b, int* lines) {
-    uint64_t r = b & (b >> 4);
-    r &= r >> 2;
-    r &= r >> 1;
-    r &= BB_COL_A;                  // bit 8*row set iff row full
-    uint64_t c = b & (b >> 32);
-    c &= c >> 16;
-    c &= c >> 8;
-    c &= 0xFFull;                   // bit col set iff column full
-    *lines = bb_popc(r) + bb_popc(c);
-    return b & ~((r * 0xFFull) | (c * BB_COL_A));
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    const uint32_t rl = bb_rowmask32(lo), rh = bb_rowmask32(hi), c = bb_fullcols(lo, hi);
+    const uint32_t cm = c * 0x01010101u;
+    *lines = ((bb_popc32(rl) + bb_popc32(rh)) >> 3) + bb_popc32(c);
+    return (uint64_t)(lo & ~(rl | cm)) | ((uint64_t)(hi & ~(rh | cm)) << 32);
 }
 
 // true iff b has at least one full row or column
 BB_HD bool bb_any_full(uint64_t b) {
-    uint64_t r = b & (b >> 4);
-    r &= r >> 2;
-    r &= r >> 1;
-    uint64_t c = b & (b >> 32);
-    c &= c >> 16;
-    c &= c >> 8;
-    return ((r & BB_COL_A) | (c & 0xFFull)) != 0;
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    return ((((bb_rowflags32(lo) | bb_rowflags32(hi)) & 0x80808080u) | bb_fullcols(lo, hi))) != 0u;
 }
 
 BB_HD uint64_t bb_clear_only(uint64_t b) {
@@ -181,16 +210,11 @@ BB_HD uint64_t bb_clear_only(uint64_t b) {
 
 // b with its full rows/columns removed; *full tells whether there were any (one pass)
 BB_HD uint64_t bb_clear_if_full(uint64_t b, bool* full) {
-    uint64_t r = b & (b >> 4);
-    r &= r >> 2;
-    r &= r >> 1;
-    r &= BB_COL_A;
-    uint64_t c = b & (b >> 32);
-    c &= c >> 16;
-    c &= c >> 8;
-    c &= 0xFFull;
-    *full = (r | c) != 0ull;
-    return b & ~((r * 0xFFull) | (c * BB_COL_A));
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    const uint32_t rl = bb_rowmask32(lo), rh = bb_rowmask32(hi), c = bb_fullcols(lo, hi);
+    const uint32_t cm = c * 0x01010101u;
+    *full = (rl | rh | c) != 0u;
+    return (uint64_t)(lo & ~(rl | cm)) | ((uint64_t)(hi & ~(rh | cm)) << 32);
 }
 
 // board.py:195-216: empty cells whose four neighbours are filled or off-board.
