@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t bb_shfl64(uint64_t v, int src) {
 // ---------------------------------------------------------------------------------------
 // Phase timers for tools/profile_phases.py (-DBB_PROFILE); BB_PF(...) vanishes in normal builds.
 #ifdef BB_PROFILE
-struct BBProf { long long cls = 0, team = 0, rounds = 0, iters = 0, t0 = 0, c0 = 0, c1 = 0, q0 = 0, q1 = 0, units = 0; };
+struct BBProf { long long cls = 0, team = 0, rounds = 0, iters = 0, t0 = 0, c0 = 0, c1 = 0, q0 = 0, q1 = 0, units = 0, units_all = 0, unit_cyc = 0; };
 __device__ unsigned long long g_pf_units = 0, g_pf_units_max = 0, g_pf_open_cyc = 0, g_pf_unit_cyc = 0, g_pf_H = 0;
 #define BB_PF(...) __VA_ARGS__
 #else
@@ -142,6 +142,7 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
             BB_PF(pf.units += 1;)
         }
         BB_PF(if (lane == 0) {
+            pf.units_all += pf.units; pf.unit_cyc += clock64() - pf.q1;
             atomicAdd(&g_pf_units, (unsigned long long)pf.units);
             atomicMax(&g_pf_units_max, (unsigned long long)pf.units);
             atomicAdd(&g_pf_open_cyc, (unsigned long long)(pf.q1 - pf.q0));
@@ -326,10 +327,13 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
                   atomicAdd(&stats[8], (unsigned long long)pf.iters);
                   atomicMax(&stats[9], tot);
                   atomicMax(&stats[10], (unsigned long long)pf.rounds);
+                  // heaviest warps: cycles << 32 | unit-loop cycles/64 << 16 | unit iterations << 8 | rounds
+                  atomicMax(&stats[63 - (tot & 7)], (tot << 32) | (((unsigned long long)pf.unit_cyc >> 6) << 16) |
+                                                        ((unsigned long long)(pf.units_all > 255 ? 255 : pf.units_all) << 8) | (unsigned long long)(pf.rounds > 255 ? 255 : pf.rounds));
                   stats[11] = g_pf_units; stats[12] = g_pf_units_max; stats[13] = g_pf_open_cyc;
                   stats[14] = g_pf_unit_cyc; stats[15] = g_pf_H;
                   atomicAdd(&stats[16 + (tot >> 13 > 31 ? 31 : tot >> 13)], 1ull);           // cycles histogram
-                  atomicAdd(&stats[48 + (pf.rounds > 15 ? 15 : pf.rounds)], 1ull);)         // rounds histogram
+                  atomicAdd(&stats[48 + (pf.rounds > 7 ? 7 : pf.rounds)], 1ull);)           // rounds histogram
             atomicAdd(&stats[0], nlive * (unsigned long long)n_steps);
             if (st_eps) {
                 atomicAdd(&stats[1], st_eps);

@@ -31,7 +31,9 @@ print("per warp-step: total cycles %.0f | classify phase %.0f | team loop %.0f |
       % (s[4] / warps, s[5] / warps, s[6] / warps, s[7] / warps, s[8] / warps))
 print("max warp cycles %d, max rounds %d" % (s[9], s[10]))
 print("per-warp cycle histogram (bins of 8192 cycles = 4.2 us):", s[16:48])
-print("team rounds per warp histogram:", s[48:64])
+print("team rounds per warp histogram:", s[48:56])
+for v in sorted(s[56:64], reverse=True):
+    print("  heavy warp: %d cycles, unit loops %d cycles, %d unit iterations, %d rounds" % (v >> 32, ((v >> 16) & 0xFFFF) << 6, (v >> 8) & 0xFF, v & 0xFF))
 R = max(s[7], 1)
 print("per round: H items %.2f | unit-loop iterations %.1f (max %d) | open cycles %.0f | unit-loop cycles %.0f (%.0f per unit)"
       % (s[15] / R, s[11] / R, s[12], s[13] / R, s[14] / R, s[14] / max(s[11], 1)))
