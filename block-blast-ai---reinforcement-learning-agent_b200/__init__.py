@@ -13,6 +13,11 @@ __version__ = "0.1.0"
 _LAZY = {
     "VectorizedBlockBlastEnv": "vec_env",
     "BlockBlastEnv": "vec_env",
+    "BlockBlastEnvFlat": "vec_env",
+    "GameState": "vec_env",
+    "Logger": "logger",
+    "TensorBoardLogger": "logger",
+    "MetricsTracker": "logger",
     "RolloutBuffer": "rollout",
     "PPOAgent": "ppo",
     "PPOConfig": "ppo",
@@ -25,6 +30,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod = importlib.import_module("." + _LAZY[name], __name__)
         return getattr(mod, name)
-    if name in ("philox", "capi", "vec_env", "rollout", "ppo", "network", "build", "dist", "train", "evaluate"):
+    if name in ("philox", "capi", "vec_env", "rollout", "ppo", "network", "build", "dist", "train", "evaluate", "logger"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import dist
+from .logger import Logger, TensorBoardLogger, tensorboard_tags
 from .ppo import PPOAgent, PPOConfig
 from .rollout import RolloutBuffer
 from .vec_env import VectorizedBlockBlastEnv
@@ -93,7 +94,9 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
     obs, _ = vec_env.reset()
     global_step, num_updates, best_score = start_step, 0, 0.0
     history = []
-    log_path = os.path.join(log_dir, "ppo_b200_%d.jsonl" % int(time.time()))
+    # same files / keys / TensorBoard tags as scripts/train.py:136-137, 231-258 (rank 0 only)
+    logger = Logger(log_dir, name="ppo_b200") if rank == 0 else None
+    tb_logger = TensorBoardLogger(log_dir, name="ppo_b200") if rank == 0 and log_c.get("tensorboard", True) else None
     t0 = time.time()
     try:
         while global_step < total_timesteps:
@@ -116,8 +119,9 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
                     best_score = avg_score
                     agent.save(os.path.join(ckpt_dir, "best.pt"))
                 if num_updates % log_interval == 0 or num_updates <= 10 or ours.get("log_every_update"):
-                    with open(log_path, "a") as f:
-                        f.write(json.dumps(row) + "\n")
+                    logger.log(row, global_step)
+                    if tb_logger is not None:
+                        tb_logger.log_metrics(tensorboard_tags(row), global_step)
                     print("update %d step=%d fps=%.0f avg_score=%.1f max=%d len=%.1f entropy=%.3f kl=%.4f clip=%.3f"
                           % (num_updates, global_step, row["fps"], avg_score, smax, row["avg_length"], metrics["entropy"],
                              metrics["approx_kl"], metrics["clip_fraction"]), flush=True)
@@ -133,6 +137,10 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
     finally:
         if rank == 0:
             agent.save(os.path.join(ckpt_dir, "final.pt"))
+            if logger.metrics_history:
+                logger.save_summary()
+            if tb_logger is not None:
+                tb_logger.close()
         vec_env.close()
     return history
 

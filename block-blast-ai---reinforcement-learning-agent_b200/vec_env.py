@@ -15,6 +15,7 @@ Output modes (``output=``):
   "packed"  CUDA tensors in the packed protocol: obs = {'board': int64[N], 'pieces': int32[N],
             'mask': int64[3,N]} — what the on-device rollout path consumes.
 """
+import dataclasses
 import os
 
 import numpy as np
@@ -439,11 +440,89 @@ class BlockBlastEnv:
         va = self.get_valid_actions()
         return int(np.random.choice(va)) if va else 0
 
+    # ---- GameState (de)serialisation over the env's slot of the batched state
+    # (GameEngine.get_state/set_state + GameState.to_dict/from_dict, engine.py:44-78, 456-476)
+    def get_state(self):
+        s = self._state()
+        board = expand_board(np.array([s["board"]]))[0].astype(np.int8)
+        p = int(s["pieces"])
+        return GameState(board=board, current_pieces=[p & 0xFF, (p >> 8) & 0xFF, (p >> 16) & 0xFF],
+                         pieces_used=[bool((p >> (24 + i)) & 1) for i in range(3)], score=int(s["score"]),
+                         combo_count=int(s["streak"]), moves_made=int(s["moves"]),
+                         status="game_over" if (int(s["aux"]) >> 16) & 1 else "playing")
+
+    def set_state(self, state):
+        """Restore board, trio, used flags, score, combo and move counters (engine.py:466-476);
+        the shaped-reward baselines (holes / centre filled) restart from the restored board, and
+        the lifetime counters the reference does not serialise keep their values."""
+        rec = self._h.get_state()
+        grid = np.asarray(state.board).astype(bool).reshape(64)
+        board = int(sum(1 << i for i in np.flatnonzero(grid)))
+        ids = [int(i) for i in state.current_pieces]
+        if len(ids) != 3 or any(not 0 <= i < 37 for i in ids):
+            raise ValueError("current_pieces must be three piece indices in [0, 37)")
+        used = sum((1 << i) for i, u in enumerate(state.pieces_used) if u)
+        over = 1 if str(getattr(state.status, "value", state.status)) == "game_over" else 0
+        rec["board"][0] = board
+        rec["pieces"][0] = ids[0] | (ids[1] << 8) | (ids[2] << 16) | (used << 24)
+        rec["aux"][0] = _holes(board) | (bin(board & 0x00003C3C3C3C0000).count("1") << 8) | (over << 16)
+        rec["score"][0], rec["streak"][0], rec["moves"][0] = state.score, state.combo_count, state.moves_made
+        self._h.set_state(rec)
+
     def render(self):
         return None
 
     def close(self):
         self._h.close()
+
+
+@dataclasses.dataclass
+class GameState:
+    """The reference's serialisable game state (engine.py:44-78): same fields, same dict layout;
+    ``status`` is the enum's string value ("playing" / "game_over")."""
+    board: np.ndarray
+    current_pieces: list
+    pieces_used: list
+    score: int
+    combo_count: int
+    moves_made: int
+    status: str = "playing"
+
+    def to_dict(self):
+        return {"board": np.asarray(self.board).tolist(), "current_pieces": list(self.current_pieces),
+                "pieces_used": list(self.pieces_used), "score": self.score, "combo_count": self.combo_count,
+                "moves_made": self.moves_made, "status": str(getattr(self.status, "value", self.status))}
+
+    @classmethod
+    def from_dict(cls, data):
+        return cls(board=np.array(data["board"], dtype=np.int8), current_pieces=list(data["current_pieces"]),
+                   pieces_used=list(data["pieces_used"]), score=data["score"], combo_count=data["combo_count"],
+                   moves_made=data["moves_made"], status=data["status"])
+
+
+class BlockBlastEnvFlat(BlockBlastEnv):
+    """Flat-observation view (block_blast_env.py:326-389): ``obs`` = board (64) + one-hot of each
+    unused piece (3 x 37, all-zero when used) + used flags (3) = 178 floats, plus ``action_mask``."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.observation_space = _DictSpace({
+            "obs": _Box(0.0, 1.0, (64 + 3 * 37 + 3,), np.float32),
+            "action_mask": _Box(0, 1, (ACTION_SPACE_SIZE,), np.int8),
+        })
+
+    def _get_observation(self):
+        base = super()._get_observation()
+        p = int(self._state()["pieces"])
+        onehot = np.zeros((3, 37), np.float32)
+        used = np.zeros(3, np.float32)
+        for i in range(3):
+            if (p >> (24 + i)) & 1:
+                used[i] = 1.0
+            else:
+                onehot[i, (p >> (8 * i)) & 0xFF] = 1.0
+        return {"obs": np.concatenate([base["board"].reshape(64), onehot.reshape(111), used]),
+                "action_mask": base["action_mask"]}
 
 
 def _holes(board):

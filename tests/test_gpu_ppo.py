@@ -263,3 +263,66 @@ def test_vectorized_env_infos_match_oracle_including_terminal_observation(torch)
                 assert "final_score" not in gi
     assert n_term > 100
     venv.close()
+
+
+def test_flat_view_and_game_state_restore(torch):
+    """BlockBlastEnvFlat (block_blast_env.py:326-389) and GameState get/set (engine.py:456-476)
+    over a slot of the batched state."""
+    import json
+    from bbgpu import philox
+    from bbgpu.vec_env import BlockBlastEnv, BlockBlastEnvFlat, GameState
+    from oracle import bb_oracle as O
+    seed = 33
+    flat = BlockBlastEnvFlat(seed=seed)
+    ref = BlockBlastEnv(seed=seed)
+    assert flat.observation_space["obs"].shape == (178,)
+    rs = np.random.RandomState(1)
+    for step in range(25):
+        fo, ro = flat._get_observation(), ref._get_observation()
+        st = ref.get_state()
+        assert fo["obs"].dtype == np.float32 and fo["obs"].shape == (178,)
+        assert np.array_equal(fo["obs"][:64], ro["board"].reshape(64))
+        assert np.array_equal(fo["action_mask"], ro["action_mask"])
+        onehot = fo["obs"][64:175].reshape(3, 37)
+        for i in range(3):
+            if st.pieces_used[i]:
+                assert onehot[i].sum() == 0 and fo["obs"][175 + i] == 1.0 and ro["pieces"][i].sum() == 0
+            else:
+                assert onehot[i].argmax() == st.current_pieces[i] and onehot[i].sum() == 1 and fo["obs"][175 + i] == 0.0
+                plane = np.zeros((8, 8), np.float32)
+                for dr, dc in O.PIECE_CELLS[st.current_pieces[i]]:
+                    plane[dr, dc] = 1.0
+                assert np.array_equal(ro["pieces"][i], plane)
+        va = ref.get_valid_actions()
+        if not va:
+            break
+        a = int(va[rs.randint(len(va))])
+        r1 = flat.step(a)
+        r2 = ref.step(a)
+        assert r1[1] == r2[1] and r1[2] == r2[2]
+        if r2[2]:
+            break
+    # serialise mid-game, restore into a fresh env with another seed: same position, same rules
+    st = ref.get_state()
+    blob = json.dumps(st.to_dict())
+    other = BlockBlastEnv(seed=999)
+    other.set_state(GameState.from_dict(json.loads(blob)))
+    o1, o2 = ref._get_observation(), other._get_observation()
+    for k in ("board", "pieces", "action_mask"):
+        assert np.array_equal(o1[k], o2[k]), k
+    i1, i2 = ref._get_info(), other._get_info()
+    assert (i1["score"], i1["moves"], i1["holes"]) == (i2["score"], i2["moves"], i2["holes"])
+    st2 = other.get_state()
+    assert st2.to_dict() == st.to_dict()
+    va = other.get_valid_actions()
+    if va and sum(st.pieces_used) < 2:        # a move that does not trigger a deal is RNG-free
+        a = va[0]
+        (oa, ra, ta, _, ia), (ob, rb, tb, _, ib) = ref.step(a), other.step(a)
+        assert ra == rb and ta == tb and np.array_equal(oa["board"], ob["board"]) and ia["score"] == ib["score"]
+    # a game-over state restores as game over: every action rejected
+    st.status = "game_over"
+    other.set_state(st)
+    _, r, t, _, info = other.step(0)
+    assert r == -10.0 and not t and info["invalid_action"] and other.get_state().status == "game_over"
+    for e in (flat, ref, other):
+        e.close()

@@ -126,3 +126,61 @@ def test_two_rank_gloo_gradient_bucket_and_scalars():
     assert l0 != l1
     assert t0 == t1 == [3.0, 30.0] and m0 == m1 == [2.0]
     assert s0 == (0, 5) and s1 == (5, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# metrics surface and GameState serialisation (item 4): host-only parts
+# ---------------------------------------------------------------------------------------------
+def test_logger_writes_reference_keys_and_summary(tmp_path):
+    import json
+    from bbgpu.logger import Logger, MetricsTracker, TensorBoardLogger, tensorboard_tags
+    lg = Logger(str(tmp_path), name="unit")
+    rows = []
+    for k in range(1, 4):
+        row = {"step": 1000 * k, "fps": 10.0 * k, "avg_score": np.float32(5 * k), "max_score": np.int64(9 * k),
+               "best_score": 5.0 * k, "avg_length": 12.5, "policy_loss": -0.01, "value_loss": 0.5, "entropy": 3.0,
+               "total_loss": 0.2, "approx_kl": 0.001, "clip_fraction": 0.05}
+        rows.append(lg.log(row, 1000 * k))
+    lines = [json.loads(l) for l in open(lg.log_file)]
+    assert len(lines) == 3 and lines[-1]["step"] == 3000 and lines[1]["avg_score"] == 10.0
+    # keys of scripts/train.py:231-243 + the record fields of src/utils/logger.py:66-71
+    for key in ("step", "time", "timestamp", "fps", "avg_score", "max_score", "best_score", "avg_length",
+                "policy_loss", "value_loss", "entropy", "approx_kl", "clip_fraction"):
+        assert key in lines[0]
+    assert lg.get_mean("fps") == 20.0 and lg.get_recent("fps", 2) == [20.0, 30.0]
+    summ = json.load(open(lg.save_summary()))
+    assert summ["total_steps"] == 3000 and summ["metrics"]["fps"] == {"mean": 20.0, "std": float(np.std([10, 20, 30])),
+                                                                     "min": 10.0, "max": 30.0, "last": 30.0}
+    tags = tensorboard_tags(rows[0])
+    assert set(tags) == {"performance/avg_score", "performance/max_score", "performance/best_score",
+                         "performance/avg_length", "performance/fps", "training/policy_loss", "training/value_loss",
+                         "training/entropy", "training/approx_kl", "training/clip_fraction"}
+    tb = TensorBoardLogger(str(tmp_path), name="tb")
+    tb.log_metrics(tags, 1000)
+    tb.log_scalars("group", {"a": 1.0, "b": 2.0}, 1000)
+    tb.close()
+    assert not tb.enabled or any(f.startswith("events.") for _, _, fs in __import__("os").walk(str(tmp_path / "tb")) for f in fs)
+    tr = MetricsTracker(window_size=3)
+    for v in (1, 2, 3, 4):
+        tr.add("episode_score", v)
+    tr.add_many("episode_length", np.array([7, 9]))
+    assert tr.get_mean("episode_score") == 3.0 and tr.get_max("episode_score") == 4.0 and tr.get_min("episode_score") == 2.0
+    assert tr.get_last("episode_length") == 9.0 and tr.get_mean("missing") == 0.0
+    assert set(tr.get_all_summaries()) == {"episode_score", "episode_length"}
+    tr.reset()
+    assert tr.get_mean("episode_score") == 0.0
+
+
+def test_game_state_dict_round_trip():
+    import json
+    from bbgpu.vec_env import GameState
+    board = np.zeros((8, 8), np.int8)
+    board[2, 3] = board[7, 7] = 1
+    gs = GameState(board=board, current_pieces=[3, 17, 36], pieces_used=[False, True, False], score=123,
+                   combo_count=2, moves_made=9, status="playing")
+    d = json.loads(json.dumps(gs.to_dict()))
+    assert set(d) == {"board", "current_pieces", "pieces_used", "score", "combo_count", "moves_made", "status"}
+    back = GameState.from_dict(d)
+    assert np.array_equal(back.board, board) and back.board.dtype == np.int8
+    assert (back.current_pieces, back.pieces_used, back.score, back.combo_count, back.moves_made, back.status) == \
+        ([3, 17, 36], [False, True, False], 123, 2, 9, "playing")
