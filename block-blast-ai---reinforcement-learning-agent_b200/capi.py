@@ -71,6 +71,7 @@ def lib():
     L.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
     L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
     L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
+    L.bb_ppo_loss.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, i64, vp]
     L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     if L.bb_version() != ABI_VERSION:
         raise BBGpuError("libbbgpu.so ABI %d != expected %d" % (L.bb_version(), ABI_VERSION))
@@ -207,6 +208,16 @@ def masked_head_backward(logits, mask, mask_stride, action, grad_logp, grad_entr
     dt = BB_BF16 if logits.dtype == torch.bfloat16 else BB_F32
     check(lib().bb_masked_head_backward(ptr(logits), dt, ptr(mask), int(mask_stride), ptr(action), ptr(grad_logp),
                                         ptr(grad_entropy), ptr(grad_logits), n, current_stream()))
+
+
+def ppo_loss(logits, mask, mask_stride, action, old_logp, adv, ret, values, clip, value_coef, entropy_coef,
+             grad_logits, grad_values, sums5):
+    import torch
+    n = logits.shape[0]
+    dt = BB_BF16 if logits.dtype == torch.bfloat16 else BB_F32
+    check(lib().bb_ppo_loss(ptr(logits), dt, ptr(mask), int(mask_stride), ptr(action), ptr(old_logp), ptr(adv), ptr(ret),
+                            ptr(values), float(clip), float(value_coef), float(entropy_coef), ptr(grad_logits),
+                            ptr(grad_values), ptr(sums5), n, current_stream()))
 
 
 def gae(rewards, values, dones, last_values, gamma, lam, adv, ret, moments=None):

@@ -292,6 +292,21 @@ int bb_masked_head_backward(const void* logits, int logits_dtype, const uint64_t
     return 0;
 }
 
+int bb_ppo_loss(const void* logits, int logits_dtype, const uint64_t* mask, int64_t mask_stride,
+                const int32_t* action, const float* old_logp, const float* advantages, const float* returns,
+                const float* values, double clip_epsilon, double value_coef, double entropy_coef,
+                void* grad_logits, float* grad_values, double* sums5, int64_t n, void* stream) {
+    if (n < 0) return fail(-1, "bb_ppo_loss: negative n");
+    if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_ppo_loss: logits_dtype must be BB_F32 or BB_BF16");
+    if (n == 0) return 0;
+    if (!logits || !mask || !action || !old_logp || !advantages || !returns || !values || !grad_logits || !grad_values || !sums5)
+        return fail(-1, "bb_ppo_loss: NULL array");
+    BB_CUDA(bb_launch_ppo_loss(logits, logits_dtype, mask, mask_stride, action, old_logp, advantages, returns, values,
+                               (float)clip_epsilon, (float)value_coef, (float)entropy_coef, grad_logits, grad_values,
+                               sums5, n, (cudaStream_t)stream), "bb_ppo_loss launch");
+    return 0;
+}
+
 int bb_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
            double gamma, double lam, float* adv, float* ret, double* moments, int64_t T, int64_t N, void* stream) {
     if (T < 0 || N < 0) return fail(-1, "bb_gae: negative size");

@@ -43,6 +43,10 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
 cudaError_t bb_launch_masked_head_bwd(const void* logits, int dtype, const uint64_t* mask, int64_t mask_stride,
                                       const int32_t* action, const float* g_logp, const float* g_ent,
                                       void* dlogits, int64_t n, cudaStream_t stream);
+cudaError_t bb_launch_ppo_loss(const void* logits, int dtype, const uint64_t* mask, int64_t mask_stride,
+                               const int32_t* action, const float* old_logp, const float* adv, const float* ret,
+                               const float* value, float clip, float value_coef, float entropy_coef,
+                               void* dlogits, float* dvalue, double* sums, int64_t n, cudaStream_t stream);
 cudaError_t bb_launch_gae(const float* rewards, const float* values, const float* dones,
                           const float* last_values, float gamma, float gamma_lam, float* adv, float* ret,
                           double* moments, int64_t T, int64_t N, cudaStream_t stream);

@@ -328,11 +328,25 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
 //   d entropy  / d z_i = -p_i (log p_i + H)
 // for valid actions i, 0 for masked ones.  Same 8-lanes-per-row layout as the forward; p is
 // recomputed from the logits (768 B read + 768 B written per row, nothing saved between passes).
-template <bool BF16>
+//
+// LOSS = true turns the same pass into the whole PPO loss tail (src/agents/ppo.py:366-395 +
+// network.py:210-262): with old log-probs, advantages, returns and the value
+// head's output it forms ratio / clipped surrogate / value MSE / entropy bonus for the row,
+// writes d(loss)/d(logits) and d(loss)/d(value) of
+//     loss = mean(-min(r A, clip(r) A)) + value_coef mean((v - R)^2) - entropy_coef mean(H)
+// directly (the loss is a mean with constant coefficients, so no second pass is needed), and adds
+// the row's terms to five double sums: -min(..), (v-R)^2, H, (r-1) - log r, [|r-1| > clip].
+struct BBPpoLossArgs {
+    const float* old_logp; const float* adv; const float* ret; const float* value;
+    float* dvalue; double* sums;
+    float clip, value_coef, entropy_coef, inv_n;
+};
+
+template <bool BF16, bool LOSS>
 __global__ void __launch_bounds__(128)
 bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
                           const int32_t* __restrict__ action, const float* __restrict__ g_logp,
-                          const float* __restrict__ g_ent, void* __restrict__ dlogits, int64_t n) {
+                          const float* __restrict__ g_ent, void* __restrict__ dlogits, int64_t n, BBPpoLossArgs L) {
     const int lane = threadIdx.x & 31;
     const int l = lane & 7;
     const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -387,8 +401,41 @@ bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __res
     for (int i = 0; i < 24; ++i) mine += (own && i == slot && ((mb >> i) & 1u)) ? exp2f(z[i] * K3_LOG2E) * inv : 0.f;
     const float pa = grp_sum(mine);
     const float eps = 1.1920928955078125e-07f;
-    const float g1 = (pa >= eps && pa <= 1.f - eps) ? g_logp[row] : 0.f;
-    const float g2 = g_ent ? g_ent[row] : 0.f;
+    float g1, g2;
+    if (LOSS) {
+        const float logp = any_valid ? logf(fminf(fmaxf(pa, eps), 1.f - eps)) : 0.f;
+        const float lr = logp - L.old_logp[row];
+        const float ratio = expf(lr);
+        const float A = L.adv[row];
+        const float s1 = ratio * A, s2 = fminf(fmaxf(ratio, 1.f - L.clip), 1.f + L.clip) * A;
+        // d min(s1, s2) / d ratio: A where the unclipped term is the minimum (ties included: inside
+        // the clip range both terms are the same function), 0 where the clipped constant is
+        const bool through = s1 < s2 || (ratio >= 1.f - L.clip && ratio <= 1.f + L.clip);
+        const float dv = L.value[row] - L.ret[row];
+        g1 = (through && pa >= eps && pa <= 1.f - eps) ? -A * ratio * L.inv_n : 0.f;
+        g2 = -L.entropy_coef * L.inv_n;
+        // per-row metric terms: lane 0 of each 8-lane group holds them, summed per warp, one
+        // atomic per warp and sum
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+        if (live && l == 0) {
+            L.dvalue[row] = 2.f * L.value_coef * dv * L.inv_n;
+            t0 = -fminf(s1, s2); t1 = dv * dv; t2 = H; t3 = (ratio - 1.f) - lr;
+            t4 = fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int d = 8; d < 32; d <<= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, d); t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, d); t3 += __shfl_xor_sync(0xffffffffu, t3, d);
+            t4 += __shfl_xor_sync(0xffffffffu, t4, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&L.sums[0], (double)t0); atomicAdd(&L.sums[1], (double)t1); atomicAdd(&L.sums[2], (double)t2);
+            atomicAdd(&L.sums[3], (double)t3); atomicAdd(&L.sums[4], (double)t4);
+        }
+    } else {
+        g1 = (pa >= eps && pa <= 1.f - eps) ? g_logp[row] : 0.f;
+        g2 = g_ent ? g_ent[row] : 0.f;
+    }
     float out[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
@@ -421,9 +468,24 @@ cudaError_t bb_launch_masked_head_bwd(const void* logits, int dtype, const uint6
                                       void* dlogits, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n * 8 + 127) / 128);
+    const BBPpoLossArgs none = {};
     if (dtype == 1)
-        bb_masked_head_bwd_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n);
+        bb_masked_head_bwd_kernel<true, false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n, none);
     else
-        bb_masked_head_bwd_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n);
+        bb_masked_head_bwd_kernel<false, false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, g_logp, g_ent, dlogits, n, none);
+    return cudaGetLastError();
+}
+
+cudaError_t bb_launch_ppo_loss(const void* logits, int dtype, const uint64_t* mask, int64_t mask_stride,
+                               const int32_t* action, const float* old_logp, const float* adv, const float* ret,
+                               const float* value, float clip, float value_coef, float entropy_coef,
+                               void* dlogits, float* dvalue, double* sums, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n * 8 + 127) / 128);
+    const BBPpoLossArgs L = {old_logp, adv, ret, value, dvalue, sums, clip, value_coef, entropy_coef, 1.0f / (float)n};
+    if (dtype == 1)
+        bb_masked_head_bwd_kernel<true, true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, nullptr, nullptr, dlogits, n, L);
+    else
+        bb_masked_head_bwd_kernel<false, true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, nullptr, nullptr, dlogits, n, L);
     return cudaGetLastError();
 }

@@ -75,6 +75,40 @@ class MaskedHead(torch.autograd.Function):
         return grad.to(ctx.in_dtype), None, None
 
 
+class PPOLossTail(torch.autograd.Function):
+    """The whole loss tail of PPOAgent.update (src/agents/ppo.py:366-395) as ONE kernel
+    (bb_ppo_loss): forward returns the scalar loss and the five metric means
+    (policy_loss, value_loss, entropy, approx_kl, clip_fraction); the gradients w.r.t. logits and
+    values are produced by the same pass and only scaled in backward."""
+
+    @staticmethod
+    def forward(ctx, logits, values, planes, action, old_logp, adv, ret, clip, value_coef, entropy_coef):
+        lg = logits.detach()
+        if lg.dtype not in (torch.float32, torch.bfloat16):
+            lg = lg.float()
+        lg = lg.contiguous()
+        n = lg.shape[0]
+        v = values.detach().float().contiguous()
+        g_logits = torch.empty_like(lg)
+        g_values = torch.empty(n, dtype=torch.float32, device=lg.device)
+        sums = torch.zeros(5, dtype=torch.float64, device=lg.device)
+        capi.ppo_loss(lg, planes, planes.stride(0), action.to(torch.int32).contiguous(), old_logp.float().contiguous(),
+                      adv.float().contiguous(), ret.float().contiguous(), v, clip, value_coef, entropy_coef,
+                      g_logits, g_values, sums)
+        means = sums / n
+        loss = (means[0] + value_coef * means[1] - entropy_coef * means[2]).float()
+        ctx.save_for_backward(g_logits, g_values)
+        ctx.dtypes = (logits.dtype, values.dtype)
+        ctx.mark_non_differentiable(means)
+        return loss, means
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_means):
+        g_logits, g_values = ctx.saved_tensors
+        return ((g_logits * g_loss).to(ctx.dtypes[0]), (g_values * g_loss).to(ctx.dtypes[1]),
+                None, None, None, None, None, None, None, None)
+
+
 class BlockBlastNetwork(nn.Module):
     def __init__(self, board_size=8, num_pieces=3, conv_channels=(64, 128, 128), fc_hidden=(512, 256),
                  action_space_size=192, use_residual=True, use_batch_norm=True):

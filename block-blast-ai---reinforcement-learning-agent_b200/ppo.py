@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import capi, dist
-from .network import BlockBlastNetwork, _pack_mask_planes
+from .network import BlockBlastNetwork, PPOLossTail, _pack_mask_planes
 from .rollout import RolloutBuffer  # noqa: F401  (re-export, as in the reference module)
 
 
@@ -36,7 +36,7 @@ class PPOConfig:
     conv_channels: Tuple[int, ...] = (64, 128, 128)
     fc_hidden: Tuple[int, ...] = (512, 256)
     precision: str = "fp32"          # "fp32" (reference numerics) | "bf16" (autocast, channels_last)
-    fused_head: bool = True          # PPO update: K3 forward + fused backward kernel instead of torch ops
+    fused_head: bool = True          # PPO update: the loss tail after the CNN as one kernel (bb_ppo_loss) instead of torch ops
 
     def to_dict(self):
         return {f.name: getattr(self, f.name) for f in fields(self)}
@@ -158,11 +158,21 @@ class PPOAgent:
             for obs, mask, actions, old_logp, adv, ret in buffer.iter_minibatches(cfg.batch_size, packed_mask=fused):
                 if cfg.precision == "bf16":
                     obs = obs.contiguous(memory_format=torch.channels_last)
+                if fused:           # mask = int64 planes [3,B]: trunk in torch, everything after it in one kernel
+                    with self._autocast():
+                        logits, values = self.network.trunk(obs)
+                    loss, means = PPOLossTail.apply(logits, values.float(), mask, actions, old_logp, adv, ret,
+                                                    cfg.clip_epsilon, cfg.value_coef, cfg.entropy_coef)
+                    self.bucket.zero()
+                    loss.backward()
+                    self.bucket.all_reduce_mean()                  # C1: one flat NCCL all-reduce
+                    nn.utils.clip_grad_norm_(self.network.parameters(), cfg.max_grad_norm)
+                    self.optimizer.step()
+                    sums += torch.stack([means[0], means[1], means[2], loss.detach().double(), means[3], means[4]])
+                    n_updates += 1
+                    continue
                 with self._autocast():
-                    if fused:       # mask = int64 planes [3,B]
-                        _, new_logp, entropy, values = self.network.evaluate_actions_fused(obs, mask, actions)
-                    else:
-                        _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
+                    _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
                 values = values.float()
                 ratio = torch.exp(new_logp - old_logp)
                 surr1 = ratio * adv

@@ -178,6 +178,19 @@ int bb_masked_head_backward(const void* logits, int logits_dtype, const uint64_t
                             int64_t mask_stride, const int32_t* action, const float* grad_logp,
                             const float* grad_entropy, void* grad_logits, int64_t n, void* stream);
 
+/* The whole PPO loss tail of one minibatch in one pass over the logits (PPOAgent.update,
+ * src/agents/ppo.py:366-395, with network.py:210-262 inside): masked log-softmax, log-prob of the
+ * stored action, ratio to old_logp, clipped surrogate, value MSE and masked-entropy bonus;
+ *   loss = mean(-min(r A, clip(r, 1-eps, 1+eps) A)) + value_coef mean((v-R)^2) - entropy_coef mean(H).
+ * Writes grad_logits[n,192] (dtype of logits) and grad_values f32[n] = d loss / d(.), and ADDS to
+ * sums5 (device f64[5], zero it first): sum of -min(..), (v-R)^2, H, (r-1)-log r, [|r-1| > eps];
+ * divide by n for policy_loss, value_loss, entropy, approx_kl, clip_fraction. */
+int bb_ppo_loss(const void* logits, int logits_dtype, const uint64_t* mask, int64_t mask_stride,
+                const int32_t* action, const float* old_logp, const float* advantages,
+                const float* returns, const float* values, double clip_epsilon, double value_coef,
+                double entropy_coef, void* grad_logits, float* grad_values, double* sums5, int64_t n,
+                void* stream);
+
 /* GAE and returns (RolloutBuffer.compute_returns_and_advantages, src/agents/ppo.py:141-169),
  * reverse scan over T, float32, same operation order as the reference (bit-identical).
  *   rewards, values, dones: device f32[T*N] time-major; last_values device f32[N]

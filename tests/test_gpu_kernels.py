@@ -235,3 +235,56 @@ def test_fused_head_backward_matches_torch_autograd(torch, dtype):
     torch.testing.assert_close(b.grad.float(), a.grad.float(), **tol)
     assert (b.grad[~dense] == 0).all() and b.grad.dtype == dt
     assert float(b.grad[0].abs().sum()) == 0.0                   # clamped at 1 - eps, like torch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_fused_ppo_loss_tail_matches_torch(torch, dtype):
+    """bb_ppo_loss (PPOLossTail) against the torch statement of src/agents/ppo.py:366-395 on top of
+    network.py:210-262: loss, the five metric means, d loss/d logits and d loss/d values."""
+    from bbgpu.network import PPOLossTail, _pack_mask_planes
+    torch.manual_seed(11)
+    n, clip, vc, ec = 6000, 0.2, 0.5, 0.01
+    dt = getattr(torch, dtype)
+    base = (torch.randn(n, 192, device="cuda") * 2).to(dt)
+    dense = (torch.rand(n, 192, device="cuda") < torch.rand(n, 1, device="cuda") * 0.6)
+    dense[torch.arange(n), torch.randint(0, 192, (n,))] = True
+    dense[0] = False; dense[0, 5] = True
+    act = (torch.rand(n, 192, device="cuda") * dense).argmax(1)
+    planes = _pack_mask_planes(dense)
+    values0 = torch.randn(n, device="cuda")
+    ret = values0 + torch.randn(n, device="cuda")
+    adv = torch.randn(n, device="cuda")
+    eps = torch.finfo(torch.float32).eps
+
+    def head(logits):
+        probs = torch.softmax(logits.float().masked_fill(~dense, float("-inf")), -1)
+        pn = probs / probs.sum(-1, keepdim=True)
+        lp = torch.log(pn.clamp(eps, 1 - eps)).gather(1, act.unsqueeze(1)).squeeze(1)
+        q = probs / probs.sum(-1, keepdim=True).clamp(min=1e-10)
+        return lp, -(q * torch.log(q.clamp(min=1e-10)) * dense).sum(-1)
+
+    with torch.no_grad():                                   # old policy = perturbed current one -> ratios on both sides of the clip
+        old_logp = head(base)[0] + 0.25 * torch.randn(n, device="cuda")
+    a, va = base.clone().requires_grad_(True), values0.clone().requires_grad_(True)
+    lp, ent = head(a)
+    ratio = torch.exp(lp - old_logp)
+    pl = -torch.min(ratio * adv, torch.clamp(ratio, 1 - clip, 1 + clip) * adv).mean()
+    vl = torch.nn.functional.mse_loss(va, ret)
+    loss_r = pl + vc * vl - ec * ent.mean()
+    loss_r.backward()
+    kl = ((ratio - 1) - torch.log(ratio)).mean()
+    cf = ((ratio - 1).abs() > clip).float().mean()
+
+    b, vb = base.clone().requires_grad_(True), values0.clone().requires_grad_(True)
+    loss_f, means = PPOLossTail.apply(b, vb, planes, act, old_logp, adv, ret, clip, vc, ec)
+    (3.0 * loss_f).backward()                               # the incoming gradient is applied
+    ref_means = torch.stack([pl, vl, ent.mean(), kl, cf]).double()
+    torch.testing.assert_close(means, ref_means.detach(), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(loss_f, loss_r.detach(), rtol=2e-5, atol=2e-6)
+    tol = dict(rtol=2e-2, atol=2e-5) if dtype == "bfloat16" else dict(rtol=2e-4, atol=2e-8)
+    torch.testing.assert_close(b.grad.float() / 3.0, a.grad.float(), **tol)
+    torch.testing.assert_close(vb.grad / 3.0, va.grad, rtol=1e-5, atol=1e-9)
+    assert (b.grad[~dense] == 0).all() and b.grad.dtype == dt and not means.requires_grad
+    frac_clipped = float(cf)
+    assert 0.05 < frac_clipped < 0.95                      # the test exercises both branches of the min
