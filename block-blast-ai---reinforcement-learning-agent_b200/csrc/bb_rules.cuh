@@ -35,8 +35,8 @@
 struct BBTables {
     uint64_t mask[BB_TABLE_N];   // piece cells at the origin (slots 37..39 are zero padding)
     uint64_t inb[BB_TABLE_N];    // anchors whose bounding box stays on the board
-    uint64_t offs[BB_TABLE_N];   // cell offsets #0..7, one byte each
-    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16 | cell offset #8 << 24
+    uint64_t offs[BB_TABLE_N];   // valid-mask recipe, one byte each: a0..a3, b1, b2 (see bb_valid)
+    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
 };
 
 #define BB_META_N(m) ((m) & 0xFu)
@@ -147,22 +147,19 @@ BB_HD uint32_t bb_byte(uint32_t w, int k) {
 }
 
 // All anchors at which piece p fits on the EMPTY-cell set e = ~board: board.py:71-93 for the
-// 64 anchors at once, one shift-AND per cell of the piece.  The offset list (a byte per cell,
-// the ninth in the meta word) is padded with repeats, so the first four steps need no predicate
-// (31 of 37 pieces have <= 4 cells).
+// 64 anchors at once.  Every piece is a Minkowski sum  A (+) {0,b1} (+) {0,b2}  of a base shape
+// of at most four cells and two doubling steps (tools/gen_piece_tables.py: the 3x3 square is
+// (0,1,2) (+) {0,8} (+) {0,8}; pieces of up to four cells have b1 = b2 = 0), so the mask is four
+// shift-ANDs of e and two shift-ANDs of the intermediate result — the same six steps for all 37
+// pieces, no branch on the piece size.  Anchors whose bounding box leaves the board are removed
+// by the in-bounds mask at the end (a shifted-in or wrapped cell can only belong to those).
 BB_HD uint64_t bb_valid(uint64_t e, const BBPiece& p) {
     const uint32_t lo = (uint32_t)p.offs, hi = (uint32_t)(p.offs >> 32);
-    uint64_t v = p.inb & bb_shr(e, bb_byte(lo, 0)) & bb_shr(e, bb_byte(lo, 1));
+    uint64_t v = bb_shr(e, bb_byte(lo, 0)) & bb_shr(e, bb_byte(lo, 1));
     v &= bb_shr(e, bb_byte(lo, 2)) & bb_shr(e, lo >> 24);
-    const uint32_t n = BB_META_N(p.meta);
-    if (n > 4) {
-        v &= bb_shr(e, bb_byte(hi, 0)) & bb_shr(e, bb_byte(hi, 1));
-        if (n > 6) {
-            v &= bb_shr(e, bb_byte(hi, 2)) & bb_shr(e, hi >> 24);
-            v &= bb_shr(e, p.meta >> 24);
-        }
-    }
-    return v;
+    v &= bb_shr(v, bb_byte(hi, 0));
+    v &= bb_shr(v, bb_byte(hi, 1));
+    return v & p.inb;
 }
 
 // Rows of a 32-bit half board (one byte per row).  A byte is 0xFF iff adding 1 to its low seven
