@@ -2,8 +2,8 @@
 //
 // One thread owns one env.  The env state is 48 B kept as three 16-byte words in three SoA
 // arrays (s0/s1/s2), so a warp reads and writes 3 x 512 contiguous bytes with 128-bit
-// accesses; all outputs are SoA too (mask planes are plane-major).  The piece tables (37 x
-// 20 B) are staged into shared memory once per block because lanes index them with
+// accesses; all outputs are SoA too (mask planes are plane-major).  The piece tables (40 x
+// 32 B) are staged into shared memory once per block because lanes index them with
 // different piece ids (constant memory would serialise divergent indices).
 //
 // Algorithmic HBM bytes per env-step (packed protocol): state 48 R + 48 W,
@@ -16,16 +16,13 @@
 #include "bb_rules.cuh"
 #include "bb_kernels.h"
 
-// statically initialised (arrays are padded to 40 entries, the tail is zero)
-__constant__ BBTables c_bb_tables = {BB_PIECE_MASKS, BB_PIECE_INB, BB_PIECE_OFFS, BB_PIECE_META};
+// statically initialised: 40 rows of 32 bytes (the last three are zero padding)
+__constant__ BBTables c_bb_tables = {BB_PIECE_ROWS};
 
 __device__ __forceinline__ void bb_stage_tables(BBTables* sh) {
-    for (int k = threadIdx.x; k < BB_TABLE_N; k += blockDim.x) {
-        sh->mask[k] = c_bb_tables.mask[k];
-        sh->inb[k] = c_bb_tables.inb[k];
-        sh->offs[k] = c_bb_tables.offs[k];
-        sh->meta[k] = c_bb_tables.meta[k];
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(&c_bb_tables);
+    uint4* dst = reinterpret_cast<uint4*>(sh);
+    for (int k = threadIdx.x; k < (int)(sizeof(BBTables) / sizeof(uint4)); k += blockDim.x) dst[k] = src[k];
     __syncthreads();
 }
 

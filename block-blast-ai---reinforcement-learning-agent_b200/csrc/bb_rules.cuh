@@ -32,12 +32,15 @@
 // tables
 // ---------------------------------------------------------------------------------------
 #define BB_TABLE_N (BB_NUM_PIECES + 3)
-struct BBTables {
-    uint64_t mask[BB_TABLE_N];   // piece cells at the origin (slots 37..39 are zero padding)
-    uint64_t inb[BB_TABLE_N];    // anchors whose bounding box stays on the board
-    uint64_t offs[BB_TABLE_N];   // valid-mask recipe, one byte each: a0..a3, b1, b2 (see bb_valid)
-    uint32_t meta[BB_TABLE_N];   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
+// one 32-byte row per piece (rows 37..39 are zero padding), so a piece is two 16-byte fetches
+struct alignas(16) BBTableRow {
+    uint64_t mask;   // piece cells at the origin
+    uint64_t inb;    // anchors whose bounding box stays on the board
+    uint64_t offs;   // valid-mask recipe, one byte each: a0..a3, b1, b2 (see bb_valid)
+    uint32_t meta;   // n | h<<4 | w<<8 | maxrow<<12 | maxcol<<16
+    uint32_t pad;
 };
+struct BBTables { BBTableRow row[BB_TABLE_N]; };
 
 #define BB_META_N(m) ((m) & 0xFu)
 #define BB_META_MAXROW(m) (((m) >> 12) & 0xFu)
@@ -50,10 +53,11 @@ static const uint32_t BB_HOST_PIECE_META[BB_NUM_PIECES] = BB_PIECE_META;
 
 inline void bb_fill_tables(BBTables* t) {
     for (int i = 0; i < BB_TABLE_N; ++i) {
-        t->mask[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_MASKS[i] : 0;
-        t->inb[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_INB[i] : 0;
-        t->offs[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_OFFS[i] : 0;
-        t->meta[i] = i < BB_NUM_PIECES ? BB_HOST_PIECE_META[i] : 0;
+        t->row[i].mask = i < BB_NUM_PIECES ? BB_HOST_PIECE_MASKS[i] : 0;
+        t->row[i].inb = i < BB_NUM_PIECES ? BB_HOST_PIECE_INB[i] : 0;
+        t->row[i].offs = i < BB_NUM_PIECES ? BB_HOST_PIECE_OFFS[i] : 0;
+        t->row[i].meta = i < BB_NUM_PIECES ? BB_HOST_PIECE_META[i] : 0;
+        t->row[i].pad = 0;
     }
 }
 
@@ -61,7 +65,16 @@ struct BBPiece { uint64_t pm, inb, offs; uint32_t meta; };
 
 BB_HD BBPiece bb_piece(const BBTables* T, uint32_t id) {
     BBPiece p;
-    p.pm = T->mask[id]; p.inb = T->inb[id]; p.offs = T->offs[id]; p.meta = T->meta[id];
+#if defined(__CUDA_ARCH__)
+    const uint4* r = reinterpret_cast<const uint4*>(&T->row[id]);
+    const uint4 a = r[0], b = r[1];
+    p.pm = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    p.inb = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    p.offs = (uint64_t)b.x | ((uint64_t)b.y << 32);
+    p.meta = b.z;
+#else
+    p.pm = T->row[id].mask; p.inb = T->row[id].inb; p.offs = T->row[id].offs; p.meta = T->row[id].meta;
+#endif
     return p;
 }
 
@@ -415,7 +428,7 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
     if (t < nA) {
         const int x = (int)(it.plan & 3u), y = (int)((it.plan >> 2) & 3u), z = (int)((it.plan >> 4) & 3u);
         const uint64_t vx = x == 0 ? it.v[0] : (x == 1 ? it.v[1] : it.v[2]);
-        const uint64_t pmx = T->mask[BB_TRIO_ID(trio, x)];
+        const uint64_t pmx = T->row[BB_TRIO_ID(trio, x)].mask;
         bool full;
         br.bb = bb_clear_if_full(it.b | (pmx << bb_select(vx, (int)t)), &full);
         br.A = bb_piece(T, BB_TRIO_ID(trio, y));
@@ -433,7 +446,7 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
     if (k >= n0) { k -= n0; i = 1; if (k >= n1) { k -= n1; i = 2; } }
     const int j = i == 0 ? 1 : 0, l = i == 2 ? 1 : 2;
     const uint64_t vi = i == 0 ? it.v[0] : (i == 1 ? it.v[1] : it.v[2]);
-    const uint64_t pmi = T->mask[BB_TRIO_ID(trio, i)];
+    const uint64_t pmi = T->row[BB_TRIO_ID(trio, i)].mask;
     bool full1;
     br.bb = bb_clear_if_full(it.b | (pmi << bb_select(vi, k)), &full1);
     br.A = bb_piece(T, BB_TRIO_ID(trio, j));
@@ -620,8 +633,8 @@ BB_HD BBMove bb_env_pre(BBState& s, int action, const BBTables* T, BBStepOut& o)
     const int a = action & 63;
     bool ok = (action >= 0) && (p < 3) && !((used >> (p & 3)) & 1u) && !BB_OVER(s);
     const uint32_t id = ok ? ((s.pieces >> (8 * p)) & 0xFFu) : 0u;
-    const uint64_t pm = T->mask[id];
-    if (ok) ok = ((T->inb[id] >> a) & 1ull) && (((pm << a) & s.board) == 0ull);
+    const uint64_t pm = T->row[id].mask;
+    if (ok) ok = ((T->row[id].inb >> a) & 1ull) && (((pm << a) & s.board) == 0ull);
     mv.ok = ok;
     o.ep_score = 0; o.ep_len = 0; o.gain = 0;
     if (!ok) {
@@ -631,7 +644,7 @@ BB_HD BBMove bb_env_pre(BBState& s, int action, const BBTables* T, BBStepOut& o)
         bb_action_mask(s, T, o.mask);
         return mv;
     }
-    const int n = (int)BB_META_N(T->meta[id]);
+    const int n = (int)BB_META_N(T->row[id].meta);
     int lines;
     s.board = bb_clear(s.board | (pm << a), &lines);
     const uint32_t used2 = used | (1u << p);
@@ -683,9 +696,9 @@ BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTab
         if (!(flags & BB_FLAG_NO_AUTO_RESET)) {
             bb_reset_state(s, seed, env_id, flags);
             // empty board, nothing used: every in-bounds anchor is valid
-            o.mask[0] = T->inb[s.pieces & 0xFFu];
-            o.mask[1] = T->inb[(s.pieces >> 8) & 0xFFu];
-            o.mask[2] = T->inb[(s.pieces >> 16) & 0xFFu];
+            o.mask[0] = T->row[s.pieces & 0xFFu].inb;
+            o.mask[1] = T->row[(s.pieces >> 8) & 0xFFu].inb;
+            o.mask[2] = T->row[(s.pieces >> 16) & 0xFFu].inb;
         }
     }
 }
