@@ -72,6 +72,10 @@ def lib():
     L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
     L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
     L.bb_ppo_loss.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, i64, vp]
+    L.bb_bn_workspace_size.restype = i64
+    L.bb_bn_workspace_size.argtypes = [C.c_int]
+    L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
+    L.bb_bn_relu_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp]
     L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     if L.bb_version() != ABI_VERSION:
         raise BBGpuError("libbbgpu.so ABI %d != expected %d" % (L.bb_version(), ABI_VERSION))
@@ -218,6 +222,27 @@ def ppo_loss(logits, mask, mask_stride, action, old_logp, adv, ret, values, clip
     check(lib().bb_ppo_loss(ptr(logits), dt, ptr(mask), int(mask_stride), ptr(action), ptr(old_logp), ptr(adv), ptr(ret),
                             ptr(values), float(clip), float(value_coef), float(entropy_coef), ptr(grad_logits),
                             ptr(grad_values), ptr(sums5), n, current_stream()))
+
+
+def bn_workspace_size(channels):
+    n = int(lib().bb_bn_workspace_size(int(channels)))
+    if n < 0:
+        raise BBGpuError("bb_bn_workspace_size: unsupported channel count %d" % channels)
+    return n
+
+
+def bn_relu_forward(x, skip, gamma, beta, running_mean, running_var, momentum, eps, training, y, save_mean, save_rstd,
+                    workspace, rows, channels):
+    check(lib().bb_bn_relu_forward(ptr(x), ptr(skip), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                   float(momentum), float(eps), int(bool(training)), ptr(y), ptr(save_mean), ptr(save_rstd),
+                                   ptr(workspace), int(rows), int(channels), current_stream()))
+
+
+def bn_relu_backward(x, y, grad_y, gamma, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta, workspace,
+                     rows, channels):
+    check(lib().bb_bn_relu_backward(ptr(x), ptr(y), ptr(grad_y), ptr(gamma), ptr(save_mean), ptr(save_rstd), ptr(grad_x),
+                                    ptr(grad_skip), ptr(grad_gamma), ptr(grad_beta), ptr(workspace), int(rows), int(channels),
+                                    current_stream()))
 
 
 def gae(rewards, values, dones, last_values, gamma, lam, adv, ret, moments=None):

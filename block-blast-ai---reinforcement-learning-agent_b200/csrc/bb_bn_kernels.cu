@@ -1,0 +1,283 @@
+// bb_bn_kernels.cu — training-mode BatchNorm + ReLU (+ residual add) for the policy CNN's
+// channels-last bf16 activations (reference src/models/network.py:14-31, 78-92: every conv of
+// the encoder is followed by BatchNorm2d + ReLU, the second one of a residual block by
+// BatchNorm2d, "+ x", ReLU).
+//
+// The convolutions stay cuDNN/PyTorch.  What is replaced is the memory-bound glue around them:
+// in the PPO update torch spends 70 % of the CNN's time in seven BatchNorm layers and their
+// ReLU / add kernels (batch_norm_collect_statistics_channels_last 0.99 ms per layer on a
+// 32,768 x 128 x 8 x 8 bf16 tensor = 0.54 TB/s).  Here a layer is
+//   forward : one read of x for the statistics, one read of x (+ skip) and one write of y
+//   backward: one read of (x, y, dy) for the two reductions, one more for dx (+ dskip)
+// with 16-byte accesses and fp32 accumulation, i.e. HBM-roofline passes over [M = N*H*W, C].
+//
+// Layout: x, y, dy, dx, skip, dskip are [M, C] bf16, C a multiple of 8 (channels-last NHWC
+// memory); gamma/beta/running stats/saved mean/rstd/dgamma/dbeta are fp32 [C].
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bb_kernels.h"
+
+#define BN_THREADS 256
+
+struct BF8 { float v[8]; };
+
+__device__ __forceinline__ BF8 bn_unpack(const uint4 q) {
+    BF8 r;
+    r.v[0] = __uint_as_float(q.x << 16); r.v[1] = __uint_as_float(q.x & 0xFFFF0000u);
+    r.v[2] = __uint_as_float(q.y << 16); r.v[3] = __uint_as_float(q.y & 0xFFFF0000u);
+    r.v[4] = __uint_as_float(q.z << 16); r.v[5] = __uint_as_float(q.z & 0xFFFF0000u);
+    r.v[6] = __uint_as_float(q.w << 16); r.v[7] = __uint_as_float(q.w & 0xFFFF0000u);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bn_pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ uint4 bn_pack(const BF8& r) {
+    return make_uint4(bn_pack2(r.v[0], r.v[1]), bn_pack2(r.v[2], r.v[3]), bn_pack2(r.v[4], r.v[5]), bn_pack2(r.v[6], r.v[7]));
+}
+
+// Two per-channel sums over the rows.  Thread t owns channel group t % G (8 channels) and walks
+// the rows t / G, t / G + R, ... of its block's share; the block folds its row lanes in shared
+// memory and writes ONE partial per channel to part[block][2][C] (no atomics: the finalize
+// kernel adds the partials in a fixed order, so results are bit-reproducible).
+//   MODE 0: sum x, sum x^2                                  (forward statistics)
+//   MODE 1: sum g, sum g * xhat, g = dy * [y > 0]           (backward reductions)
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+bb_bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ part,
+                    int64_t M, int C) {
+    extern __shared__ float sh[];                      // [R][2][C]
+    const int G = C >> 3, R = BN_THREADS / G;
+    const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+    float a[8], b[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; mu[k] = 0.f; rs[k] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mu[k] = mean[g * 8 + k]; rs[k] = rstd[g * 8 + k]; }
+    }
+    if (r0 < R) {
+        for (int64_t row = (int64_t)blockIdx.x * R + r0; row < M; row += (int64_t)gridDim.x * R) {
+            const BF8 xv = bn_unpack(__ldg(x + row * G + g));
+            if (MODE == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { a[k] += xv.v[k]; b[k] = fmaf(xv.v[k], xv.v[k], b[k]); }
+            } else {
+                const BF8 yv = bn_unpack(__ldg(y + row * G + g));
+                const BF8 dv = bn_unpack(__ldg(dy + row * G + g));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gk = yv.v[k] > 0.f ? dv.v[k] : 0.f;
+                    a[k] += gk;
+                    b[k] = fmaf(gk, (xv.v[k] - mu[k]) * rs[k], b[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sh[(r0 * 2 + 0) * C + g * 8 + k] = a[k]; sh[(r0 * 2 + 1) * C + g * 8 + k] = b[k]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += sh[r * 2 * C + c];
+        part[(int64_t)blockIdx.x * 2 * C + c] = s;
+    }
+}
+
+// forward finalize: mean / rstd of the batch, running statistics (momentum update with the
+// unbiased variance, as torch.nn.BatchNorm2d), and the affine pair y = x * scale + shift
+__global__ void bb_bn_finalize_fwd_kernel(const float* __restrict__ part, int nblocks, int64_t M, int C, float eps,
+                                          float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                          float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) { s += (double)part[(int64_t)b * 2 * C + c]; q += (double)part[(int64_t)b * 2 * C + C + c]; }
+    const double mu = s / (double)M;
+    double var = q / (double)M - mu * mu;
+    var = var > 0.0 ? var : 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    save_mean[c] = (float)mu;
+    save_rstd[c] = rstd;
+    if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mu * sc;
+}
+
+// eval mode: the affine pair from the running statistics
+__global__ void bb_bn_affine_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                         float eps, int C, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - running_mean[c] * sc;
+}
+
+// y = relu(x * scale + shift (+ skip)); four rows in flight per thread
+__global__ void __launch_bounds__(BN_THREADS)
+bb_bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ scale,
+                   const float* __restrict__ shift, uint4* __restrict__ y, int64_t M, int C) {
+    const int G = C >> 3, R = BN_THREADS / G;
+    const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+    if (r0 >= R) return;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[g * 8 + k]; sf[k] = shift[g * 8 + k]; }
+    const int64_t stride = (int64_t)gridDim.x * R;
+    for (int64_t row = (int64_t)blockIdx.x * R + r0; row < M; row += 4 * stride) {
+        uint4 xq[4], sq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                xq[u] = __ldg(x + rr * G + g);
+                if (skip) sq[u] = __ldg(skip + rr * G + g);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                BF8 v = bn_unpack(xq[u]);
+                if (skip) {
+                    const BF8 s = bn_unpack(sq[u]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc[k], sf[k]) + s.v[k], 0.f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc[k], sf[k]), 0.f);
+                }
+                y[rr * G + g] = bn_pack(v);
+            }
+        }
+    }
+}
+
+// backward finalize: dgamma, dbeta and the per-channel coefficients of
+//   dx = scale * (g - c1 - xhat * c2),  c1 = sum g / M,  c2 = sum g xhat / M
+__global__ void bb_bn_finalize_bwd_kernel(const float* __restrict__ part, int nblocks, int64_t M, int C,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                          float* __restrict__ c1, float* __restrict__ c2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) { s += (double)part[(int64_t)b * 2 * C + c]; q += (double)part[(int64_t)b * 2 * C + C + c]; }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)q;
+    c1[c] = (float)(s / (double)M);
+    c2[c] = (float)(q / (double)M);
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bb_bn_dx_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
+                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                const float* __restrict__ c1, const float* __restrict__ c2, uint4* __restrict__ dx,
+                uint4* __restrict__ dskip, int64_t M, int C) {
+    const int G = C >> 3, R = BN_THREADS / G;
+    const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+    if (r0 >= R) return;
+    float mu[8], rs[8], sc[8], k1[8], k2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        mu[k] = mean[c]; rs[k] = rstd[c]; sc[k] = gamma[c] * rs[k]; k1[k] = c1[c]; k2[k] = c2[c];
+    }
+    const int64_t stride = (int64_t)gridDim.x * R;
+    for (int64_t row = (int64_t)blockIdx.x * R + r0; row < M; row += 2 * stride) {
+        uint4 xq[2], yq[2], dq[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) { xq[u] = __ldg(x + rr * G + g); yq[u] = __ldg(y + rr * G + g); dq[u] = __ldg(dy + rr * G + g); }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t rr = row + u * stride;
+            if (rr < M) {
+                const BF8 xv = bn_unpack(xq[u]), yv = bn_unpack(yq[u]), dv = bn_unpack(dq[u]);
+                BF8 gv, ov;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    gv.v[k] = yv.v[k] > 0.f ? dv.v[k] : 0.f;
+                    ov.v[k] = sc[k] * (gv.v[k] - k1[k] - (xv.v[k] - mu[k]) * rs[k] * k2[k]);
+                }
+                dx[rr * G + g] = bn_pack(ov);
+                if (dskip) dskip[rr * G + g] = bn_pack(gv);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers.  Workspace (floats): part[grid][2][C] | scale[C] | shift[C] (forward) or c1[C] | c2[C]
+// ---------------------------------------------------------------------------------------
+static int bn_grid() {
+    static int grid = 0;
+    if (!grid) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        grid = (sms > 0 ? sms : 148) * 8;                  // 8 resident blocks of 256 threads per SM
+    }
+    return grid;
+}
+
+size_t bb_bn_workspace_floats(int C) { return (size_t)bn_grid() * 2 * C + 2 * (size_t)C; }
+
+cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps, int training,
+                                  void* y, float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
+                                  cudaStream_t stream) {
+    const int grid = bn_grid();
+    float* part = workspace;
+    float* scale = workspace + (size_t)grid * 2 * C;
+    float* shift = scale + C;
+    const int R = BN_THREADS / (C >> 3);
+    const int64_t need = (M + R - 1) / R;
+    const int g = (int)(need < grid ? need : grid);
+    if (training) {
+        bb_bn_reduce_kernel<0><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
+            (const uint4*)x, nullptr, nullptr, nullptr, nullptr, part, M, C);
+        bb_bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g, M, C, eps, momentum, gamma, beta, running_mean,
+                                                                      running_var, save_mean, save_rstd, scale, shift);
+    } else {
+        bb_bn_affine_eval_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C, scale, shift);
+    }
+    const int64_t need4 = (need + 3) / 4;
+    bb_bn_apply_kernel<<<(int)(need4 < grid ? (need4 > 0 ? need4 : 1) : grid), BN_THREADS, 0, stream>>>(
+        (const uint4*)x, (const uint4*)skip, scale, shift, (uint4*)y, M, C);
+    return cudaGetLastError();
+}
+
+cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma,
+                                  const float* save_mean, const float* save_rstd, void* dx, void* dskip,
+                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream) {
+    const int grid = bn_grid();
+    float* part = workspace;
+    float* c1 = workspace + (size_t)grid * 2 * C;
+    float* c2 = c1 + C;
+    const int R = BN_THREADS / (C >> 3);
+    const int64_t need = (M + R - 1) / R;
+    const int g = (int)(need < grid ? need : grid);
+    bb_bn_reduce_kernel<1><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
+        (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, part, M, C);
+    bb_bn_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g, M, C, dgamma, dbeta, c1, c2);
+    const int64_t need2 = (need + 1) / 2;
+    bb_bn_dx_kernel<<<(int)(need2 < grid ? (need2 > 0 ? need2 : 1) : grid), BN_THREADS, 0, stream>>>(
+        (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, gamma, c1, c2, (uint4*)dx, (uint4*)dskip, M, C);
+    return cudaGetLastError();
+}

@@ -307,6 +307,42 @@ int bb_ppo_loss(const void* logits, int logits_dtype, const uint64_t* mask, int6
     return 0;
 }
 
+int64_t bb_bn_workspace_size(int channels) {
+    if (channels <= 0 || channels % 8 != 0 || channels > 2048) return -1;
+    return (int64_t)bb_bn_workspace_floats(channels);
+}
+
+static int bn_check(int64_t rows, int channels) {
+    if (rows < 0) return fail(-1, "bb_bn_relu: negative rows");
+    if (channels <= 0 || channels % 8 != 0 || channels > 2048) return fail(-1, "bb_bn_relu: channels must be a multiple of 8 in [8, 2048]");
+    return 0;
+}
+
+int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, double momentum, double eps, int training, void* y, float* save_mean,
+                       float* save_rstd, float* workspace, int64_t rows, int channels, void* stream) {
+    if (bn_check(rows, channels)) return -1;
+    if (rows == 0) return 0;
+    if (!x || !gamma || !beta || !y || !workspace) return fail(-1, "bb_bn_relu_forward: NULL array");
+    if (training && (!save_mean || !save_rstd)) return fail(-1, "bb_bn_relu_forward: training needs save_mean / save_rstd");
+    if (!training && (!running_mean || !running_var)) return fail(-1, "bb_bn_relu_forward: eval needs the running statistics");
+    BB_CUDA(bb_launch_bn_relu_fwd(x, skip, gamma, beta, running_mean, running_var, (float)momentum, (float)eps, training, y,
+                                  save_mean, save_rstd, workspace, rows, channels, (cudaStream_t)stream), "bb_bn_relu_forward launch");
+    return 0;
+}
+
+int bb_bn_relu_backward(const void* x, const void* y, const void* grad_y, const float* gamma, const float* save_mean,
+                        const float* save_rstd, void* grad_x, void* grad_skip, float* grad_gamma, float* grad_beta,
+                        float* workspace, int64_t rows, int channels, void* stream) {
+    if (bn_check(rows, channels)) return -1;
+    if (rows == 0) return 0;
+    if (!x || !y || !grad_y || !gamma || !save_mean || !save_rstd || !grad_x || !grad_gamma || !grad_beta || !workspace)
+        return fail(-1, "bb_bn_relu_backward: NULL array");
+    BB_CUDA(bb_launch_bn_relu_bwd(x, y, grad_y, gamma, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta, workspace,
+                                  rows, channels, (cudaStream_t)stream), "bb_bn_relu_backward launch");
+    return 0;
+}
+
 int bb_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
            double gamma, double lam, float* adv, float* ret, double* moments, int64_t T, int64_t N, void* stream) {
     if (T < 0 || N < 0) return fail(-1, "bb_gae: negative size");

@@ -8,7 +8,7 @@
 #define BB_STEP_THREADS 128
 #endif
 #ifndef BB_STEP_MIN_BLOCKS
-#define BB_STEP_MIN_BLOCKS 4
+#define BB_STEP_MIN_BLOCKS 6
 #endif
 
 // device-side view of a batch of envs (SoA of 16-byte words, see bb_rules.cuh BBState)
@@ -50,3 +50,11 @@ cudaError_t bb_launch_ppo_loss(const void* logits, int dtype, const uint64_t* ma
 cudaError_t bb_launch_gae(const float* rewards, const float* values, const float* dones,
                           const float* last_values, float gamma, float gamma_lam, float* adv, float* ret,
                           double* moments, int64_t T, int64_t N, cudaStream_t stream);
+size_t bb_bn_workspace_floats(int C);
+cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps, int training,
+                                  void* y, float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
+                                  cudaStream_t stream);
+cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma,
+                                  const float* save_mean, const float* save_rstd, void* dx, void* dskip,
+                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream);

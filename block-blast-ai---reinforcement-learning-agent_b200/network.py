@@ -18,8 +18,71 @@ import torch.nn.functional as F
 from . import capi
 
 
+_BN_WORKSPACE = {}
+
+
+def _bn_workspace(channels, device):
+    key = (device.index, channels)
+    ws = _BN_WORKSPACE.get(key)
+    if ws is None:
+        ws = _BN_WORKSPACE[key] = torch.empty(capi.bn_workspace_size(channels), dtype=torch.float32, device=device)
+    return ws
+
+
+class FusedBNReLU(torch.autograd.Function):
+    """relu(BatchNorm2d(x) (+ skip)) on channels-last bf16 activations as HBM-roofline passes
+    (bb_bn_relu_forward / bb_bn_relu_backward) instead of torch's batch_norm + add + relu kernels;
+    the module keeps its nn.BatchNorm2d parameters and buffers (running statistics are updated in
+    place exactly like torch: momentum, unbiased variance)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, weight, bias, running_mean, running_var, training, momentum, eps):
+        x = x.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        rows = n * h * w
+        if skip is not None:
+            skip = skip.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = torch.empty_like(x)
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        capi.bn_relu_forward(x, skip, weight, bias, running_mean, running_var, momentum, eps, training, y,
+                             save_mean, save_rstd, _bn_workspace(c, x.device), rows, c)
+        ctx.save_for_backward(x, y, weight, save_mean, save_rstd)
+        ctx.has_skip = skip is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, y, weight, save_mean, save_rstd = ctx.saved_tensors
+        n, c, h, w = x.shape
+        grad_y = grad_y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        grad_x = torch.empty_like(x)
+        grad_skip = torch.empty_like(x) if ctx.has_skip else None
+        grad_gamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        grad_beta = torch.empty(c, dtype=torch.float32, device=x.device)
+        capi.bn_relu_backward(x, y, grad_y, weight, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta,
+                              _bn_workspace(c, x.device), n * h * w, c)
+        return grad_x, grad_skip, grad_gamma, grad_beta, None, None, None, None, None
+
+
+def bn_relu(bn, x, skip=None, fused=False):
+    """relu(bn(x) (+ skip)); the fused kernels when asked for and applicable (CUDA, bf16, channel
+    count a multiple of 8, affine BatchNorm with running statistics, training mode or no autograd)."""
+    if (fused and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0 and bn.affine
+            and bn.track_running_stats and bn.momentum is not None and (bn.training or not torch.is_grad_enabled())):
+        if bn.training:
+            bn.num_batches_tracked.add_(1)
+        return FusedBNReLU.apply(x, skip, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training,
+                                 bn.momentum, bn.eps)
+    y = bn(x)
+    if skip is not None:
+        y = y + skip
+    return F.relu(y)
+
+
 class ResidualBlock(nn.Module):
     """conv-bn-relu-conv-bn + skip, relu (reference network.py:14-31)."""
+    fused_bn = False
 
     def __init__(self, channels):
         super().__init__()
@@ -29,9 +92,8 @@ class ResidualBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(channels)
 
     def forward(self, x):
-        y = F.relu(self.bn1(self.conv1(x)))
-        y = self.bn2(self.conv2(y))
-        return F.relu(y + x)
+        y = bn_relu(self.bn1, self.conv1(x), None, self.fused_bn)
+        return bn_relu(self.bn2, self.conv2(y), x, self.fused_bn)
 
 
 def _pack_mask_planes(mask_dense):
@@ -140,9 +202,32 @@ class BlockBlastNetwork(nn.Module):
                     nn.init.zeros_(m.bias)
 
     # ---------------------------------------------------------------- body
+    def set_fused_bn(self, on=True):
+        """Route every BatchNorm2d + ReLU (+ residual add) of the encoder through FusedBNReLU."""
+        self.fused_bn = bool(on)
+        for m in self.modules():
+            if isinstance(m, ResidualBlock):
+                m.fused_bn = bool(on)
+        return self
+
+    def _encode(self, x):
+        if not getattr(self, "fused_bn", False):
+            return self.conv_encoder(x)
+        mods = list(self.conv_encoder)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.BatchNorm2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                x = bn_relu(m, x, None, True)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
+
     def trunk(self, x):
         """x: (B,4,8,8) = cat([board, pieces]) (network.py:152-158) -> (raw logits (B,192), value (B,))."""
-        x = self.conv_encoder(x)
+        x = self._encode(x)
         x = self.fc_encoder(x.flatten(1))
         return self.policy_head(x), self.value_head(x).squeeze(-1)
 

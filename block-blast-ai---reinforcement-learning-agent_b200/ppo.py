@@ -36,6 +36,7 @@ class PPOConfig:
     conv_channels: Tuple[int, ...] = (64, 128, 128)
     fc_hidden: Tuple[int, ...] = (512, 256)
     precision: str = "fp32"          # "fp32" (reference numerics) | "bf16" (autocast, channels_last)
+    fused_bn: bool = True            # bf16 only: BatchNorm + ReLU (+ residual add) as bb_bn_relu_* kernels around cuDNN's convs
     fused_head: bool = True          # PPO update: the loss tail after the CNN as one kernel (bb_ppo_loss) instead of torch ops
 
     def to_dict(self):
@@ -60,6 +61,7 @@ class PPOAgent:
                                          fc_hidden=tuple(self.config.fc_hidden)).to(self.device)
         if self.config.precision == "bf16":
             self.network = self.network.to(memory_format=torch.channels_last)
+            self.network.set_fused_bn(self.config.fused_bn)
             torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the conv algorithms
         dist.broadcast_module(self.network)
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5)
@@ -199,7 +201,7 @@ class PPOAgent:
     # ------------------------------------------------------------------ persistence / modes
     def save(self, path):
         """Same keys as ppo.py:425-431 so the reference's evaluate.py / GUI can load it."""
-        cfgd = {k: v for k, v in self.config.to_dict().items() if k not in ("precision", "fused_head")}
+        cfgd = {k: v for k, v in self.config.to_dict().items() if k not in ("precision", "fused_head", "fused_bn")}
         torch.save({"network_state_dict": self.network.state_dict(),
                     "optimizer_state_dict": self.optimizer.state_dict(), "config": cfgd}, path)
 
@@ -210,7 +212,7 @@ class PPOAgent:
             self.optimizer.load_state_dict(ck["optimizer_state_dict"])
         if "config" in ck:
             self.config = PPOConfig.from_dict({**ck["config"], "precision": self.config.precision,
-                                               "fused_head": self.config.fused_head})
+                                               "fused_head": self.config.fused_head, "fused_bn": self.config.fused_bn})
         self.bucket.rebind()
 
     def train(self):

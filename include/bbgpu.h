@@ -191,6 +191,29 @@ int bb_ppo_loss(const void* logits, int logits_dtype, const uint64_t* mask, int6
                 double entropy_coef, void* grad_logits, float* grad_values, double* sums5, int64_t n,
                 void* stream);
 
+/* BatchNorm2d + ReLU (+ residual add) of the policy CNN on channels-last bf16 activations
+ * (src/models/network.py:14-31 ResidualBlock, :78-92 conv encoder: conv -> BatchNorm2d -> ReLU, and
+ * conv -> BatchNorm2d -> "+ x" -> ReLU).  The convolutions stay cuDNN; these two calls replace
+ * torch's batch_norm / relu / add kernels around them with HBM-roofline passes.
+ *   x, skip, y, grad_*: device bf16 [rows, channels], rows = N*H*W (NHWC memory), channels % 8 == 0
+ *   gamma, beta, running_*, save_*, grad_gamma, grad_beta: device f32 [channels]
+ *   workspace: device f32 [bb_bn_workspace_size(channels)]
+ * forward : training != 0: batch statistics (biased variance for the normalisation, running
+ *           statistics updated with momentum and the unbiased variance like torch.nn.BatchNorm2d),
+ *           save_mean / save_rstd written for backward; training == 0: running statistics.
+ *           y = relu((x - mean) * rstd * gamma + beta (+ skip)); skip may be NULL.
+ * backward: g = grad_y * [y > 0]; grad_beta = sum g; grad_gamma = sum g * xhat;
+ *           grad_x = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)); grad_skip = g (NULL to skip). */
+int64_t bb_bn_workspace_size(int channels);
+int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, double momentum, double eps,
+                       int training, void* y, float* save_mean, float* save_rstd, float* workspace,
+                       int64_t rows, int channels, void* stream);
+int bb_bn_relu_backward(const void* x, const void* y, const void* grad_y, const float* gamma,
+                        const float* save_mean, const float* save_rstd, void* grad_x, void* grad_skip,
+                        float* grad_gamma, float* grad_beta, float* workspace, int64_t rows,
+                        int channels, void* stream);
+
 /* GAE and returns (RolloutBuffer.compute_returns_and_advantages, src/agents/ppo.py:141-169),
  * reverse scan over T, float32, same operation order as the reference (bit-identical).
  *   rewards, values, dones: device f32[T*N] time-major; last_values device f32[N]

@@ -288,3 +288,119 @@ def test_fused_ppo_loss_tail_matches_torch(torch, dtype):
     assert (b.grad[~dense] == 0).all() and b.grad.dtype == dt and not means.requires_grad
     frac_clipped = float(cf)
     assert 0.05 < frac_clipped < 0.95                      # the test exercises both branches of the min
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,with_skip", [((96, 64, 8, 8), False), ((64, 128, 8, 8), True), ((7, 128, 8, 8), True),
+                                             ((33, 24, 3, 5), False)])
+def test_fused_bn_relu_matches_torch(torch, shape, with_skip):
+    """bb_bn_relu_forward/backward (FusedBNReLU) against torch's batch_norm (+ skip) + relu with
+    autograd, both on bf16 channels-last activations (network.py:14-31, 78-92), incl. the running
+    statistics update and eval mode."""
+    import torch.nn.functional as F
+    from bbgpu.network import FusedBNReLU
+    torch.manual_seed(5)
+    n, c, h, w = shape
+    x0 = (torch.randn(shape, device="cuda") * 1.7 + 0.4).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    s0 = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if with_skip else None
+    gamma0, beta0 = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
+    gy = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def run(fused):
+        x = x0.clone().requires_grad_(True)
+        s = s0.clone().requires_grad_(True) if with_skip else None
+        g, b = gamma0.clone().requires_grad_(True), beta0.clone().requires_grad_(True)
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        if fused:
+            y = FusedBNReLU.apply(x, s, g, b, rm, rv, True, 0.1, 1e-5)
+        else:                                       # fp32 maths on the same bf16 inputs = the exact answer
+            z = F.batch_norm(x.float(), rm, rv, g, b, True, 0.1, 1e-5)
+            if with_skip:
+                z = z + s.float()
+            y = F.relu(z)
+        y.backward(gy.to(y.dtype))
+        return y.detach().float(), x.grad.float(), (s.grad.float() if with_skip else None), g.grad, b.grad, rm, rv
+
+    yf, dxf, dsf, dgf, dbf, rmf, rvf = run(True)
+    yr, dxr, dsr, dgr, dbr, rmr, rvr = run(False)
+    torch.testing.assert_close(yf, yr, rtol=1e-2, atol=1e-2)                       # bf16 output rounding
+    torch.testing.assert_close(rmf, rmr, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rvf, rvr, rtol=1e-4, atol=1e-6)
+    # the relu mask comes from the bf16 output: entries with |y| below bf16 resolution may flip, so
+    # compare the gradients in aggregate and elementwise with a small budget of mismatches
+    bad = ((dxf - dxr).abs() > 2e-2 + 2e-2 * dxr.abs()).float().mean()
+    assert float(bad) < 2e-3
+    torch.testing.assert_close(dgf, dgr, rtol=2e-2, atol=2e-2 * float(dgr.abs().max()))
+    torch.testing.assert_close(dbf, dbr, rtol=2e-2, atol=2e-2 * float(dbr.abs().max()))
+    if with_skip:
+        assert float(((dsf - dsr).abs() > 1e-2).float().mean()) < 2e-3
+    # eval mode uses the running statistics and leaves them alone
+    rm, rv = torch.randn(c, device="cuda") * 0.2, torch.rand(c, device="cuda") + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    with torch.no_grad():
+        ye = FusedBNReLU.apply(x0, s0, gamma0, beta0, rm, rv, False, 0.1, 1e-5).float()
+        ze = F.batch_norm(x0.float(), rm, rv, gamma0, beta0, False, 0.1, 1e-5)
+        ze = F.relu(ze + s0.float()) if with_skip else F.relu(ze)
+    torch.testing.assert_close(ye, ze, rtol=1e-2, atol=1e-2)
+    assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
+
+
+@pytest.mark.gpu
+def test_network_with_fused_bn_matches_torch_path(torch):
+    """The whole trunk with FusedBNReLU, bf16 autocast + channels-last as PPOAgent(precision='bf16')
+    runs it.  Two bf16 pipelines differ from each other by their rounding noise, so both are
+    measured against the fp32 network with the same weights: the fused path must be as close to it
+    as torch's own bf16 path (outputs, parameter gradients, BatchNorm buffers)."""
+    import copy
+    from bbgpu.network import BlockBlastNetwork
+    torch.manual_seed(9)
+    base = BlockBlastNetwork().cuda()
+    for m in base.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    x = (torch.rand(1024, 4, 8, 8, device="cuda") < 0.4).float()
+
+    def run(net, bf16):
+        net.train()
+        xin = x.contiguous(memory_format=torch.channels_last) if bf16 else x
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            logits, value = net.trunk(xin)
+        (logits.float().pow(2).mean() + value.float().mean()).backward()
+        return (logits.float().detach(), value.float().detach(), {k: p.grad.float() for k, p in net.named_parameters()},
+                {k: b.float().clone() for k, b in net.named_buffers()})
+
+    ref = run(copy.deepcopy(base), False)
+    tor = run(copy.deepcopy(base).to(memory_format=torch.channels_last), True)
+    fus_net = copy.deepcopy(base).to(memory_format=torch.channels_last).set_fused_bn(True)
+    fus = run(fus_net, True)
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-12))
+
+    for i in (0, 1):
+        assert rel(fus[i], ref[i]) < max(1.5 * rel(tor[i], ref[i]), 0.02), (i, rel(fus[i], ref[i]), rel(tor[i], ref[i]))
+    worst = 0.0
+    scale = max(float(g.norm()) for g in ref[2].values())
+    for k in ref[2]:
+        if float(ref[2][k].norm()) < 1e-4 * scale:
+            # a conv bias in front of a BatchNorm has zero true gradient (the mean is removed):
+            # what is left is rounding noise on every path, compare it in absolute terms
+            assert float(fus[2][k].norm()) < max(2.0 * float(tor[2][k].norm()), 1e-3 * scale), k
+            continue
+        ef, et = rel(fus[2][k], ref[2][k]), rel(tor[2][k], ref[2][k])
+        assert ef < max(1.5 * et, 0.03), (k, ef, et)
+        worst = max(worst, ef)
+    assert worst < 0.25
+    for k in ref[3]:
+        if k.endswith("num_batches_tracked"):
+            assert float(fus[3][k]) == float(ref[3][k]) == 1.0
+        else:
+            assert rel(fus[3][k], ref[3][k]) < max(1.5 * rel(tor[3][k], ref[3][k]), 0.01), k
+    # eval mode (deterministic evaluation) goes through the running statistics
+    tor_net = copy.deepcopy(fus_net).set_fused_bn(False)
+    fus_net.eval(); tor_net.eval()
+    xin = x.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        la, _ = tor_net.trunk(xin)
+        lb, _ = fus_net.trunk(xin)
+    assert rel(lb.float(), la.float()) < 0.03
