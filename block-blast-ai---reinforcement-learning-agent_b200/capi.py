@@ -74,7 +74,7 @@ def lib():
     L.bb_ppo_loss.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, i64, vp]
     L.bb_bn_workspace_size.restype = i64
     L.bb_bn_workspace_size.argtypes = [C.c_int]
-    L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
+    L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
     L.bb_bn_relu_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp]
     L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     if L.bb_version() != ABI_VERSION:
@@ -231,9 +231,9 @@ def bn_workspace_size(channels):
     return n
 
 
-def bn_relu_forward(x, skip, gamma, beta, running_mean, running_var, momentum, eps, training, y, save_mean, save_rstd,
-                    workspace, rows, channels):
-    check(lib().bb_bn_relu_forward(ptr(x), ptr(skip), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+def bn_relu_forward(x, skip, gamma, beta, pre_bias, running_mean, running_var, momentum, eps, training, y, save_mean,
+                    save_rstd, workspace, rows, channels):
+    check(lib().bb_bn_relu_forward(ptr(x), ptr(skip), ptr(gamma), ptr(beta), ptr(pre_bias), ptr(running_mean), ptr(running_var),
                                    float(momentum), float(eps), int(bool(training)), ptr(y), ptr(save_mean), ptr(save_rstd),
                                    ptr(workspace), int(rows), int(channels), current_stream()))
 

@@ -89,17 +89,28 @@ bb_bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
     }
 }
 
+// one warp per channel adds that channel's two partial sums over the blocks (lanes stride over the
+// blocks, fixed order, double accumulation)
+__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ part, int nblocks, int C, int c, double& s, double& q) {
+    const int lane = threadIdx.x & 31;
+    s = 0.0; q = 0.0;
+    for (int b = lane; b < nblocks; b += 32) { s += (double)part[(int64_t)b * 2 * C + c]; q += (double)part[(int64_t)b * 2 * C + C + c]; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
+}
+
 // forward finalize: mean / rstd of the batch, running statistics (momentum update with the
 // unbiased variance, as torch.nn.BatchNorm2d), and the affine pair y = x * scale + shift
 __global__ void bb_bn_finalize_fwd_kernel(const float* __restrict__ part, int nblocks, int64_t M, int C, float eps,
                                           float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                          const float* __restrict__ pre_bias, float* __restrict__ running_mean, float* __restrict__ running_var,
                                           float* __restrict__ save_mean, float* __restrict__ save_rstd,
                                           float* __restrict__ scale, float* __restrict__ shift) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) { s += (double)part[(int64_t)b * 2 * C + c]; q += (double)part[(int64_t)b * 2 * C + C + c]; }
+    double s, q;
+    bn_sum_partials(part, nblocks, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     const double mu = s / (double)M;
     double var = q / (double)M - mu * mu;
     var = var > 0.0 ? var : 0.0;
@@ -108,7 +119,9 @@ __global__ void bb_bn_finalize_fwd_kernel(const float* __restrict__ part, int nb
     save_rstd[c] = rstd;
     if (running_mean) {
         const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+        // a per-channel bias the caller left out of x (the conv bias: BatchNorm cancels it in y)
+        // still belongs to the mean the module tracks
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mu + (pre_bias ? pre_bias[c] : 0.f));
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
     const float sc = gamma[c] * rstd;
@@ -118,13 +131,13 @@ __global__ void bb_bn_finalize_fwd_kernel(const float* __restrict__ part, int nb
 
 // eval mode: the affine pair from the running statistics
 __global__ void bb_bn_affine_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                         const float* __restrict__ pre_bias, const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                          float eps, int C, float* __restrict__ scale, float* __restrict__ shift) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
     scale[c] = sc;
-    shift[c] = beta[c] - running_mean[c] * sc;
+    shift[c] = beta[c] + ((pre_bias ? pre_bias[c] : 0.f) - running_mean[c]) * sc;
 }
 
 // y = relu(x * scale + shift (+ skip)); four rows in flight per thread
@@ -172,10 +185,11 @@ bb_bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, 
 __global__ void bb_bn_finalize_bwd_kernel(const float* __restrict__ part, int nblocks, int64_t M, int C,
                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
                                           float* __restrict__ c1, float* __restrict__ c2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) { s += (double)part[(int64_t)b * 2 * C + c]; q += (double)part[(int64_t)b * 2 * C + C + c]; }
+    double s, q;
+    bn_sum_partials(part, nblocks, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)q;
     c1[c] = (float)(s / (double)M);
@@ -239,7 +253,7 @@ static int bn_grid() {
 size_t bb_bn_workspace_floats(int C) { return (size_t)bn_grid() * 2 * C + 2 * (size_t)C; }
 
 cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* gamma, const float* beta,
-                                  float* running_mean, float* running_var, float momentum, float eps, int training,
+                                  const float* pre_bias, float* running_mean, float* running_var, float momentum, float eps, int training,
                                   void* y, float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
                                   cudaStream_t stream) {
     const int grid = bn_grid();
@@ -252,10 +266,10 @@ cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* 
     if (training) {
         bb_bn_reduce_kernel<0><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
             (const uint4*)x, nullptr, nullptr, nullptr, nullptr, part, M, C);
-        bb_bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g, M, C, eps, momentum, gamma, beta, running_mean,
-                                                                      running_var, save_mean, save_rstd, scale, shift);
+        bb_bn_finalize_fwd_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(part, g, M, C, eps, momentum, gamma, beta, pre_bias,
+                                                                      running_mean, running_var, save_mean, save_rstd, scale, shift);
     } else {
-        bb_bn_affine_eval_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C, scale, shift);
+        bb_bn_affine_eval_kernel<<<(C + 127) / 128, 128, 0, stream>>>(gamma, beta, pre_bias, running_mean, running_var, eps, C, scale, shift);
     }
     const int64_t need4 = (need + 3) / 4;
     bb_bn_apply_kernel<<<(int)(need4 < grid ? (need4 > 0 ? need4 : 1) : grid), BN_THREADS, 0, stream>>>(
@@ -275,7 +289,7 @@ cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, 
     const int g = (int)(need < grid ? need : grid);
     bb_bn_reduce_kernel<1><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
         (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, part, M, C);
-    bb_bn_finalize_bwd_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g, M, C, dgamma, dbeta, c1, c2);
+    bb_bn_finalize_bwd_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(part, g, M, C, dgamma, dbeta, c1, c2);
     const int64_t need2 = (need + 1) / 2;
     bb_bn_dx_kernel<<<(int)(need2 < grid ? (need2 > 0 ? need2 : 1) : grid), BN_THREADS, 0, stream>>>(
         (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, gamma, c1, c2, (uint4*)dx, (uint4*)dskip, M, C);

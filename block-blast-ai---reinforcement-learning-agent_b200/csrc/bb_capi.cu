@@ -318,7 +318,8 @@ static int bn_check(int64_t rows, int channels) {
     return 0;
 }
 
-int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, const float* beta, float* running_mean,
+int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, const float* beta, const float* pre_bias,
+                       float* running_mean,
                        float* running_var, double momentum, double eps, int training, void* y, float* save_mean,
                        float* save_rstd, float* workspace, int64_t rows, int channels, void* stream) {
     if (bn_check(rows, channels)) return -1;
@@ -326,7 +327,7 @@ int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, cons
     if (!x || !gamma || !beta || !y || !workspace) return fail(-1, "bb_bn_relu_forward: NULL array");
     if (training && (!save_mean || !save_rstd)) return fail(-1, "bb_bn_relu_forward: training needs save_mean / save_rstd");
     if (!training && (!running_mean || !running_var)) return fail(-1, "bb_bn_relu_forward: eval needs the running statistics");
-    BB_CUDA(bb_launch_bn_relu_fwd(x, skip, gamma, beta, running_mean, running_var, (float)momentum, (float)eps, training, y,
+    BB_CUDA(bb_launch_bn_relu_fwd(x, skip, gamma, beta, pre_bias, running_mean, running_var, (float)momentum, (float)eps, training, y,
                                   save_mean, save_rstd, workspace, rows, channels, (cudaStream_t)stream), "bb_bn_relu_forward launch");
     return 0;
 }

@@ -52,7 +52,7 @@ cudaError_t bb_launch_gae(const float* rewards, const float* values, const float
                           double* moments, int64_t T, int64_t N, cudaStream_t stream);
 size_t bb_bn_workspace_floats(int C);
 cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* gamma, const float* beta,
-                                  float* running_mean, float* running_var, float momentum, float eps, int training,
+                                  const float* pre_bias, float* running_mean, float* running_var, float momentum, float eps, int training,
                                   void* y, float* save_mean, float* save_rstd, float* workspace, int64_t M, int C,
                                   cudaStream_t stream);
 cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma,

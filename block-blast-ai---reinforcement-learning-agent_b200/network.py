@@ -36,7 +36,7 @@ class FusedBNReLU(torch.autograd.Function):
     place exactly like torch: momentum, unbiased variance)."""
 
     @staticmethod
-    def forward(ctx, x, skip, weight, bias, running_mean, running_var, training, momentum, eps):
+    def forward(ctx, x, skip, weight, bias, running_mean, running_var, training, momentum, eps, pre_bias=None):
         x = x.contiguous(memory_format=torch.channels_last)
         n, c, h, w = x.shape
         rows = n * h * w
@@ -45,7 +45,8 @@ class FusedBNReLU(torch.autograd.Function):
         y = torch.empty_like(x)
         save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
         save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-        capi.bn_relu_forward(x, skip, weight, bias, running_mean, running_var, momentum, eps, training, y,
+        pb = None if pre_bias is None else pre_bias.detach().float().contiguous()
+        capi.bn_relu_forward(x, skip, weight, bias, pb, running_mean, running_var, momentum, eps, training, y,
                              save_mean, save_rstd, _bn_workspace(c, x.device), rows, c)
         ctx.save_for_backward(x, y, weight, save_mean, save_rstd)
         ctx.has_skip = skip is not None
@@ -62,22 +63,42 @@ class FusedBNReLU(torch.autograd.Function):
         grad_beta = torch.empty(c, dtype=torch.float32, device=x.device)
         capi.bn_relu_backward(x, y, grad_y, weight, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta,
                               _bn_workspace(c, x.device), n * h * w, c)
-        return grad_x, grad_skip, grad_gamma, grad_beta, None, None, None, None, None
+        return grad_x, grad_skip, grad_gamma, grad_beta, None, None, None, None, None, None
 
 
-def bn_relu(bn, x, skip=None, fused=False):
+def _bn_fusable(bn, channels):
+    return (channels % 8 == 0 and bn.affine and bn.track_running_stats and bn.momentum is not None
+            and (bn.training or not torch.is_grad_enabled()))
+
+
+def bn_relu(bn, x, skip=None, fused=False, pre_bias=None):
     """relu(bn(x) (+ skip)); the fused kernels when asked for and applicable (CUDA, bf16, channel
-    count a multiple of 8, affine BatchNorm with running statistics, training mode or no autograd)."""
-    if (fused and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0 and bn.affine
-            and bn.track_running_stats and bn.momentum is not None and (bn.training or not torch.is_grad_enabled())):
+    count a multiple of 8, affine BatchNorm with running statistics, training mode or no autograd).
+    ``pre_bias``: conv bias the caller left out of x (see conv_bn_relu)."""
+    if fused and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and _bn_fusable(bn, x.shape[1]):
         if bn.training:
             bn.num_batches_tracked.add_(1)
         return FusedBNReLU.apply(x, skip, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training,
-                                 bn.momentum, bn.eps)
+                                 bn.momentum, bn.eps, pre_bias)
+    if pre_bias is not None:
+        x = x + pre_bias.to(x.dtype).view(1, -1, 1, 1)
     y = bn(x)
     if skip is not None:
         y = y + skip
     return F.relu(y)
+
+
+def conv_bn_relu(conv, bn, x, skip=None, fused=False):
+    """relu(bn(conv(x)) (+ skip)).  On the fused path the convolution runs WITHOUT its bias:
+    BatchNorm subtracts the batch mean, so a per-channel constant in front of it cancels exactly in
+    the output and its gradient is identically zero; the bias is handed to the BatchNorm kernel,
+    which keeps it in the tracked running mean (and applies it in eval mode).  This removes the
+    bias-add and bias-gradient passes over the activations (15 % and 9 % of the CNN's time)."""
+    if (fused and x.is_cuda and conv.bias is not None and _bn_fusable(bn, conv.out_channels)
+            and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return bn_relu(bn, y, skip, True, conv.bias)
+    return bn_relu(bn, conv(x), skip, fused)
 
 
 class ResidualBlock(nn.Module):
@@ -92,8 +113,8 @@ class ResidualBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(channels)
 
     def forward(self, x):
-        y = bn_relu(self.bn1, self.conv1(x), None, self.fused_bn)
-        return bn_relu(self.bn2, self.conv2(y), x, self.fused_bn)
+        y = conv_bn_relu(self.conv1, self.bn1, x, None, self.fused_bn)
+        return conv_bn_relu(self.conv2, self.bn2, y, x, self.fused_bn)
 
 
 def _pack_mask_planes(mask_dense):
@@ -217,7 +238,11 @@ class BlockBlastNetwork(nn.Module):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, nn.BatchNorm2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+            if (isinstance(m, nn.Conv2d) and i + 2 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d)
+                    and isinstance(mods[i + 2], nn.ReLU)):
+                x = conv_bn_relu(m, mods[i + 1], x, None, True)
+                i += 3
+            elif isinstance(m, nn.BatchNorm2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
                 x = bn_relu(m, x, None, True)
                 i += 2
             else:

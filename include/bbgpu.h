@@ -202,11 +202,15 @@ int bb_ppo_loss(const void* logits, int logits_dtype, const uint64_t* mask, int6
  *           statistics updated with momentum and the unbiased variance like torch.nn.BatchNorm2d),
  *           save_mean / save_rstd written for backward; training == 0: running statistics.
  *           y = relu((x - mean) * rstd * gamma + beta (+ skip)); skip may be NULL.
+ *           pre_bias (f32 [channels] or NULL): a per-channel constant the caller did NOT add to x
+ *           — the bias of the convolution in front, which BatchNorm cancels in y — so the conv's
+ *           bias-add and bias-gradient passes disappear; it is added to the tracked running mean
+ *           (training) and to x (eval) so the module behaves exactly as conv(bias) -> BatchNorm.
  * backward: g = grad_y * [y > 0]; grad_beta = sum g; grad_gamma = sum g * xhat;
  *           grad_x = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)); grad_skip = g (NULL to skip). */
 int64_t bb_bn_workspace_size(int channels);
 int bb_bn_relu_forward(const void* x, const void* skip, const float* gamma, const float* beta,
-                       float* running_mean, float* running_var, double momentum, double eps,
+                       const float* pre_bias, float* running_mean, float* running_var, double momentum, double eps,
                        int training, void* y, float* save_mean, float* save_rstd, float* workspace,
                        int64_t rows, int channels, void* stream);
 int bb_bn_relu_backward(const void* x, const void* y, const void* grad_y, const float* gamma,

@@ -343,6 +343,22 @@ def test_fused_bn_relu_matches_torch(torch, shape, with_skip):
         ze = F.relu(ze + s0.float()) if with_skip else F.relu(ze)
     torch.testing.assert_close(ye, ze, rtol=1e-2, atol=1e-2)
     assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
+    # pre_bias = a conv bias left out of x: cancels in the training output, is tracked by the running
+    # mean, and is applied in eval mode — i.e. identical to batch_norm(x + bias)
+    pb = torch.randn(c, device="cuda")
+    rm1, rv1 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    with torch.no_grad():
+        y1 = FusedBNReLU.apply(x0, s0, gamma0, beta0, rm1, rv1, True, 0.1, 1e-5, pb).float()
+        z2 = F.batch_norm(x0.float() + pb.view(1, -1, 1, 1), rm2, rv2, gamma0, beta0, True, 0.1, 1e-5)
+        z2 = F.relu(z2 + s0.float()) if with_skip else F.relu(z2)
+        torch.testing.assert_close(y1, z2, rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(rm1, rm2, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(rv1, rv2, rtol=1e-4, atol=1e-6)
+        y3 = FusedBNReLU.apply(x0, s0, gamma0, beta0, rm, rv, False, 0.1, 1e-5, pb).float()
+        z3 = F.batch_norm(x0.float() + pb.view(1, -1, 1, 1), rm, rv, gamma0, beta0, False, 0.1, 1e-5)
+        z3 = F.relu(z3 + s0.float()) if with_skip else F.relu(z3)
+        torch.testing.assert_close(y3, z3, rtol=1e-2, atol=2e-2)
 
 
 @pytest.mark.gpu
@@ -358,6 +374,8 @@ def test_network_with_fused_bn_matches_torch_path(torch):
     for m in base.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
+        if isinstance(m, torch.nn.Conv2d):                 # the reference zero-initialises biases; make them count
+            torch.nn.init.normal_(m.bias, std=0.3)
     x = (torch.rand(1024, 4, 8, 8, device="cuda") < 0.4).float()
 
     def run(net, bf16):
@@ -366,7 +384,7 @@ def test_network_with_fused_bn_matches_torch_path(torch):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
             logits, value = net.trunk(xin)
         (logits.float().pow(2).mean() + value.float().mean()).backward()
-        return (logits.float().detach(), value.float().detach(), {k: p.grad.float() for k, p in net.named_parameters()},
+        return (logits.float().detach(), value.float().detach(), {k: (p.grad.float() if p.grad is not None else torch.zeros_like(p)) for k, p in net.named_parameters()},
                 {k: b.float().clone() for k, b in net.named_buffers()})
 
     ref = run(copy.deepcopy(base), False)
