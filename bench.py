@@ -283,12 +283,32 @@ def kernel_rooflines(dev, peak):
                                  "frac_of_hbm_peak": b / t / 1e9 / peak}
     for k in ("K2_unpack_obs_f32", "K2_unpack_obs_bf16"):
         out[k]["frac_of_write_only_fill"] = out[k]["achieved_GBs"] / out["write_only_fill_GBs"]
+    del board, pieces, obs, obs16
+    # BatchNorm + ReLU + residual add of the CNN (bf16 NHWC [rows, 128]): forward reads x twice and the
+    # skip once, writes y; backward reads (x, y, dy) twice, writes dx and dskip
+    rows, ch = 32768 * 64, 128
+    mk = lambda: torch.randn(rows, ch, device=dev).to(torch.bfloat16)
+    x, skip, y, dy, dx, dsk = mk(), mk(), mk(), mk(), mk(), mk()
+    gamma, beta = torch.rand(ch, device=dev) + 0.5, torch.randn(ch, device=dev)
+    rm, rv = torch.zeros(ch, device=dev), torch.ones(ch, device=dev)
+    sm, sr = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
+    dg, db = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
+    ws = torch.empty(capi.bn_workspace_size(ch), device=dev)
+    t = timeit(lambda: capi.bn_relu_forward(x, skip, gamma, beta, None, rm, rv, 0.1, 1e-5, True, y, sm, sr, ws, rows, ch))
+    b = 4 * rows * ch * 2
+    out["BN_relu_residual_forward_bf16"] = {"rows": rows, "channels": ch, "us": t * 1e6, "algorithmic_bytes": b,
+                                            "achieved_GBs": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / peak}
+    t = timeit(lambda: capi.bn_relu_backward(x, y, dy, gamma, sm, sr, dx, dsk, dg, db, ws, rows, ch))
+    b = 8 * rows * ch * 2
+    out["BN_relu_residual_backward_bf16"] = {"rows": rows, "channels": ch, "us": t * 1e6, "algorithmic_bytes": b,
+                                             "achieved_GBs": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / peak}
     return out
 
 
 def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk):
     """Masked-PPO collect + GAE + update on the device-resident path (BASELINE config 4 shape:
-    131,072 envs per GPU); returns samples/s and the phase times.  One warm-up iteration."""
+    131,072 envs per GPU); returns samples/s and the phase times.  Two warm-up iterations (cuDNN
+    autotuning of the conv shapes happens in the first, allocator growth in the second)."""
     import torch
     import torch.distributed as dist
     from bbgpu.ppo import PPOAgent, PPOConfig
@@ -303,7 +323,7 @@ def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk
     orig_act = agent.act
     agent.act = lambda o, deterministic=False: orig_act(o, deterministic, chunk)
     times = {}
-    for it in range(2):
+    for it in range(3):
         ep = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(4)]
         if world > 1:
             dist.barrier()
@@ -326,7 +346,8 @@ def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk
     return dict(samples_per_sec=world * n_envs * T / float(tt.item()), envs_per_gpu=n_envs, rollout_steps=T,
                 minibatch=minibatch, epochs=epochs, precision=precision, act_chunk=chunk, **times,
                 entropy=metrics["entropy"], approx_kl=metrics["approx_kl"],
-                network="BlockBlastNetwork 5,290,113 params (PyTorch/cuDNN, not one of our kernels)",
+                network="BlockBlastNetwork 5,290,113 params: convs/linears cuDNN/cuBLAS via PyTorch; BatchNorm+ReLU(+residual) "
+                        "= bb_bn_relu_* kernels, loss tail = bb_ppo_loss (bf16 path)",
                 grad_allreduce="1 flat NCCL all-reduce of 21.2 MB per optimiser step" if world > 1 else "n/a (1 GPU)")
 
 
@@ -532,7 +553,7 @@ def main():
     torch.cuda.empty_cache()
     if not args.no_ppo:
         ppo = gpu_ppo_leg(rank, world, dev, args.ppo_envs, args.ppo_steps, args.ppo_minibatch, args.ppo_epochs,
-                          args.ppo_precision, 32768)
+                          args.ppo_precision, None)
 
     if rank == 0:
         peak, peak_src = load_peaks()
