@@ -250,10 +250,27 @@ class BlockBlastNetwork(nn.Module):
                 i += 1
         return x
 
+    def _flatten_fc(self, x):
+        """fc_encoder(x.flatten(1)).  The first Linear's weight is laid out for the NCHW flatten
+        (state_dict compatibility); for channels-last activations x.flatten(1) is a 2 x 0.5 GB
+        transposing copy per 32,768-sample minibatch (forward + backward), so the 8 MB weight is
+        permuted to (h, w, c) order instead and the activations are used as they lie in memory."""
+        fc0 = self.fc_encoder[0]
+        if (getattr(self, "fused_bn", False) and x.dim() == 4 and isinstance(fc0, nn.Linear)
+                and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()):
+            b, c, h, w = x.shape
+            flat = x.permute(0, 2, 3, 1).reshape(b, h * w * c)                                  # a view
+            wperm = fc0.weight.view(fc0.out_features, c, h, w).permute(0, 2, 3, 1).reshape(fc0.out_features, h * w * c)
+            y = F.linear(flat, wperm, fc0.bias)
+            for m in list(self.fc_encoder)[1:]:
+                y = m(y)
+            return y
+        return self.fc_encoder(x.flatten(1))
+
     def trunk(self, x):
         """x: (B,4,8,8) = cat([board, pieces]) (network.py:152-158) -> (raw logits (B,192), value (B,))."""
         x = self._encode(x)
-        x = self.fc_encoder(x.flatten(1))
+        x = self._flatten_fc(x)
         return self.policy_head(x), self.value_head(x).squeeze(-1)
 
     @staticmethod
