@@ -64,7 +64,9 @@ class PPOAgent:
             self.network.set_fused_bn(self.config.fused_bn)
             torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the conv algorithms
         dist.broadcast_module(self.network)
-        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5)
+        # fused=True: one multi-tensor kernel per step instead of a foreach sequence (same update rule)
+        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5,
+                                          fused=self.device.type == "cuda")
         self.scheduler = None
         self.bucket = dist.FlatGradBucket(self.network.parameters())
 
@@ -168,7 +170,7 @@ class PPOAgent:
                     self.bucket.zero()
                     loss.backward()
                     self.bucket.all_reduce_mean()                  # C1: one flat NCCL all-reduce
-                    nn.utils.clip_grad_norm_(self.network.parameters(), cfg.max_grad_norm)
+                    self.bucket.clip_grad_norm_(cfg.max_grad_norm)
                     self.optimizer.step()
                     sums += torch.stack([means[0], means[1], means[2], loss.detach().double(), means[3], means[4]])
                     n_updates += 1
@@ -186,7 +188,7 @@ class PPOAgent:
                 self.bucket.zero()
                 loss.backward()
                 self.bucket.all_reduce_mean()                      # C1: one flat NCCL all-reduce
-                nn.utils.clip_grad_norm_(self.network.parameters(), cfg.max_grad_norm)
+                self.bucket.clip_grad_norm_(cfg.max_grad_norm)
                 self.optimizer.step()
                 with torch.no_grad():
                     approx_kl = ((ratio - 1) - torch.log(ratio)).mean()

@@ -184,3 +184,23 @@ def test_game_state_dict_round_trip():
     assert np.array_equal(back.board, board) and back.board.dtype == np.int8
     assert (back.current_pieces, back.pieces_used, back.score, back.combo_count, back.moves_made, back.status) == \
         ([3, 17, 36], [False, True, False], 123, 2, 9, "playing")
+
+
+def test_flat_bucket_clip_matches_torch_clip_grad_norm():
+    import torch
+    from bbgpu.dist import FlatGradBucket
+    torch.manual_seed(0)
+    for scale in (0.01, 30.0):                      # below and above the threshold
+        lin = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+        ref.load_state_dict(lin.state_dict())
+        bucket = FlatGradBucket(lin.parameters())
+        x = torch.randn(11, 7) * scale
+        lin(x).pow(2).sum().backward()
+        ref(x).pow(2).sum().backward()
+        n1 = bucket.clip_grad_norm_(0.5)
+        n2 = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        torch.testing.assert_close(n1, n2)
+        for a, b in zip(lin.parameters(), ref.parameters()):
+            assert a.grad.data_ptr() >= bucket.flat.data_ptr()          # still views of the bucket
+            torch.testing.assert_close(a.grad, b.grad)
