@@ -72,6 +72,7 @@ def lib():
     L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
     L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
     L.bb_ppo_loss.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, i64, vp]
+    L.bb_env_host_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
     L.bb_bn_workspace_size.restype = i64
     L.bb_bn_workspace_size.argtypes = [C.c_int]
     L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
@@ -185,6 +186,34 @@ class EnvHandle:
                   info=None):
         check(lib().bb_env_step_host(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(board), ptr(pieces),
                                      ptr(mask), ptr(ep_score), ptr(ep_len), ptr(info), current_stream()))
+
+
+HOST_LAYOUT_FIELDS = ("mask", "board", "rewards", "pieces", "ep_score", "ep_len", "info", "term")
+
+
+def host_layout(n_envs):
+    """({field: byte offset}, total bytes) of the single-block result layout of bb_env_step_host."""
+    offs = (C.c_int64 * 8)()
+    total = C.c_int64()
+    check(lib().bb_env_host_layout(int(n_envs), offs, C.byref(total)))
+    return dict(zip(HOST_LAYOUT_FIELDS, [int(o) for o in offs])), int(total.value)
+
+
+def pinned_result_block(n_envs):
+    """One pinned host block laid out for bb_env_step_host, as a dict of typed torch views
+    (mask int64 [3,n], board int64, rewards f32, pieces int32, ep_score, ep_len, info int32, term u8)."""
+    import torch
+    offs, total = host_layout(n_envs)
+    block = torch.zeros(total, dtype=torch.uint8).pin_memory()
+    n = int(n_envs)
+    dt = dict(mask=(torch.int64, 3 * n), board=(torch.int64, n), rewards=(torch.float32, n), pieces=(torch.int32, n),
+              ep_score=(torch.int32, n), ep_len=(torch.int32, n), info=(torch.int32, n), term=(torch.uint8, n))
+    out = {"_block": block}
+    for k, (t, cnt) in dt.items():
+        nbytes = cnt * torch.empty(0, dtype=t).element_size()
+        out[k] = block[offs[k]:offs[k] + nbytes].view(t)
+    out["mask"] = out["mask"].view(3, n)
+    return out
 
 
 def unpack_obs(board, pieces, mask, mask_stride, obs=None, mask_dense=None, n=None):

@@ -31,6 +31,7 @@ struct bb_env {
     int32_t* d_ep_score;
     int32_t* d_ep_len;
     uint32_t* d_info;
+    uint8_t* d_block;      // the eight result arrays above live in this one allocation (bb_env_host_layout)
 };
 
 static const double BB_DEFAULT_CFG[7] = {1.0, 0.01, -1.0, -0.05, 0.02, 0.5, 0.001};
@@ -93,8 +94,7 @@ int bb_env_create(bb_env** out, int64_t n_envs, uint64_t seed, int64_t global_en
 int bb_env_destroy(bb_env* e) {
     if (!e) return 0;
     cudaFree(e->arr.s0); cudaFree(e->arr.s1); cudaFree(e->arr.s2);
-    cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_terminated); cudaFree(e->d_board);
-    cudaFree(e->d_pieces); cudaFree(e->d_mask); cudaFree(e->d_ep_score); cudaFree(e->d_ep_len); cudaFree(e->d_info);
+    cudaFree(e->d_actions); cudaFree(e->d_block);
     delete e;
     return 0;
 }
@@ -204,21 +204,36 @@ int bb_env_set_state(bb_env* e, const void* host_records, void* stream) {
     return 0;
 }
 
+// Result arrays of the host-buffer step, as byte offsets into ONE block of `total` bytes:
+// [0] mask u64[3][n], [1] board u64[n], [2] rewards f32[n], [3] pieces u32[n], [4] ep_score i32[n],
+// [5] ep_len i32[n], [6] info u32[n], [7] terminated u8[n].  A caller whose eight host arrays sit
+// in one pinned block at these offsets gets them with a single device-to-host copy.
+int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes) {
+    if (n_envs <= 0 || !offsets8 || !total_bytes) return fail(-1, "bb_env_host_layout: bad argument");
+    const int64_t n = n_envs;
+    offsets8[0] = 0; offsets8[1] = 24 * n; offsets8[2] = 32 * n; offsets8[3] = 36 * n; offsets8[4] = 40 * n;
+    offsets8[5] = 44 * n; offsets8[6] = 48 * n; offsets8[7] = 52 * n;
+    *total_bytes = 53 * n;
+    return 0;
+}
+
 static int ensure_staging(bb_env* e) {
     if (e->d_actions) return 0;
     const int64_t n = e->arr.n;
+    int64_t off[8], total;
+    bb_env_host_layout(n, off, &total);
     cudaError_t err = cudaMalloc(&e->d_actions, n * sizeof(int32_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_rewards, n * sizeof(float));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_terminated, n);
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_board, n * sizeof(uint64_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_pieces, n * sizeof(uint32_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_mask, 3 * n * sizeof(uint64_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_ep_score, n * sizeof(int32_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_ep_len, n * sizeof(int32_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_info, n * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_block, (size_t)total);
     if (err != cudaSuccess) return fail(-2, "bb_env_step_host: cudaMalloc staging", err);
-    cudaMemset(e->d_ep_score, 0, n * sizeof(int32_t));
-    cudaMemset(e->d_ep_len, 0, n * sizeof(int32_t));
+    cudaMemset(e->d_block, 0, (size_t)total);
+    e->d_mask = (uint64_t*)(e->d_block + off[0]);
+    e->d_board = (uint64_t*)(e->d_block + off[1]);
+    e->d_rewards = (float*)(e->d_block + off[2]);
+    e->d_pieces = (uint32_t*)(e->d_block + off[3]);
+    e->d_ep_score = (int32_t*)(e->d_block + off[4]);
+    e->d_ep_len = (int32_t*)(e->d_block + off[5]);
+    e->d_info = (uint32_t*)(e->d_block + off[6]);
+    e->d_terminated = e->d_block + off[7];
     return 0;
 }
 
@@ -231,21 +246,31 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
     const int64_t n = e->arr.n;
     cudaStream_t s = (cudaStream_t)stream;
     BB_CUDA(cudaMemcpyAsync(e->d_actions, h_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s), "H2D actions");
-    BB_CUDA(bb_launch_step(e->arr, e->cfg, e->d_actions, e->d_rewards, e->d_terminated, h_mask ? e->d_mask : nullptr,
-                           h_ep_score ? e->d_ep_score : nullptr, h_ep_len ? e->d_ep_len : nullptr,
-                           h_info ? e->d_info : nullptr, s),
+    // the step kernel writes the packed next observation (board, pieces) itself
+    BB_CUDA(bb_launch_step_range(e->arr, e->cfg, 0, n, e->d_actions, e->d_rewards, e->d_terminated,
+                                 h_mask ? e->d_mask : nullptr, h_ep_score ? e->d_ep_score : nullptr,
+                                 h_ep_len ? e->d_ep_len : nullptr, h_info ? e->d_info : nullptr,
+                                 h_board ? e->d_board : nullptr, h_pieces ? e->d_pieces : nullptr, s),
             "bb_env_step_host launch");
-    if (h_board || h_pieces)
-        BB_CUDA(bb_launch_observe(e->arr, h_board ? e->d_board : nullptr, h_pieces ? e->d_pieces : nullptr, nullptr, s),
-                "bb_env_step_host observe");
-    BB_CUDA(cudaMemcpyAsync(h_rewards, e->d_rewards, n * sizeof(float), cudaMemcpyDeviceToHost, s), "D2H rewards");
-    BB_CUDA(cudaMemcpyAsync(h_terminated, e->d_terminated, n, cudaMemcpyDeviceToHost, s), "D2H terminated");
-    if (h_board) BB_CUDA(cudaMemcpyAsync(h_board, e->d_board, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s), "D2H board");
-    if (h_pieces) BB_CUDA(cudaMemcpyAsync(h_pieces, e->d_pieces, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H pieces");
-    if (h_mask) BB_CUDA(cudaMemcpyAsync(h_mask, e->d_mask, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s), "D2H mask");
-    if (h_ep_score) BB_CUDA(cudaMemcpyAsync(h_ep_score, e->d_ep_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_score");
-    if (h_ep_len) BB_CUDA(cudaMemcpyAsync(h_ep_len, e->d_ep_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_len");
-    if (h_info) BB_CUDA(cudaMemcpyAsync(h_info, e->d_info, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H info");
+    int64_t off[8], total;
+    bb_env_host_layout(n, off, &total);
+    uint8_t* hb = (uint8_t*)h_mask;
+    const bool one_block = hb && (uint8_t*)h_board == hb + off[1] && (uint8_t*)h_rewards == hb + off[2] &&
+                           (uint8_t*)h_pieces == hb + off[3] && (uint8_t*)h_ep_score == hb + off[4] &&
+                           (uint8_t*)h_ep_len == hb + off[5] && (uint8_t*)h_info == hb + off[6] && h_terminated == hb + off[7];
+    if (one_block) {
+        // one 53 B/env transfer instead of eight calls (each costs several microseconds of driver time)
+        BB_CUDA(cudaMemcpyAsync(hb, e->d_block, (size_t)total, cudaMemcpyDeviceToHost, s), "D2H results");
+    } else {
+        BB_CUDA(cudaMemcpyAsync(h_rewards, e->d_rewards, n * sizeof(float), cudaMemcpyDeviceToHost, s), "D2H rewards");
+        BB_CUDA(cudaMemcpyAsync(h_terminated, e->d_terminated, n, cudaMemcpyDeviceToHost, s), "D2H terminated");
+        if (h_board) BB_CUDA(cudaMemcpyAsync(h_board, e->d_board, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s), "D2H board");
+        if (h_pieces) BB_CUDA(cudaMemcpyAsync(h_pieces, e->d_pieces, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H pieces");
+        if (h_mask) BB_CUDA(cudaMemcpyAsync(h_mask, e->d_mask, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s), "D2H mask");
+        if (h_ep_score) BB_CUDA(cudaMemcpyAsync(h_ep_score, e->d_ep_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_score");
+        if (h_ep_len) BB_CUDA(cudaMemcpyAsync(h_ep_len, e->d_ep_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_len");
+        if (h_info) BB_CUDA(cudaMemcpyAsync(h_info, e->d_info, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H info");
+    }
     BB_CUDA(cudaStreamSynchronize(s), "bb_env_step_host sync");
     return 0;
 }

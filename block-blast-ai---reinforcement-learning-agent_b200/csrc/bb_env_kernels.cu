@@ -230,7 +230,8 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
                int32_t* __restrict__ actions_out, float* __restrict__ rewards,
                uint8_t* __restrict__ terminated, uint64_t* __restrict__ mask_out,
                int32_t* __restrict__ ep_score, int32_t* __restrict__ ep_len,
-               uint32_t* __restrict__ info_out, unsigned long long* __restrict__ stats) {
+               uint32_t* __restrict__ info_out, unsigned long long* __restrict__ stats,
+               uint64_t* __restrict__ board_out, uint32_t* __restrict__ pieces_out) {
     __shared__ BBTables T;
     bb_stage_tables(&T);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,15 +296,18 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         if (rewards) rewards[i] = o.reward;
         if (terminated) terminated[i] = (uint8_t)o.terminated;
         if (mask_out) {
+            const int64_t ms = E.out_stride ? E.out_stride : E.n;
             mask_out[i] = o.mask[0];
-            mask_out[E.n + i] = o.mask[1];
-            mask_out[2 * E.n + i] = o.mask[2];
+            mask_out[ms + i] = o.mask[1];
+            mask_out[2 * ms + i] = o.mask[2];
         }
         if (o.terminated) {
             if (ep_score) ep_score[i] = o.ep_score;
             if (ep_len) ep_len[i] = o.ep_len;
         }
         if (info_out) info_out[i] = o.info;
+        if (board_out) board_out[i] = s.board;          // the next observation (packed)
+        if (pieces_out) pieces_out[i] = s.pieces;
     }
     if (RANDOM && stats) {
         // warp-reduce (redux.sync on the 32-bit halves), one atomic per warp per counter
@@ -414,7 +418,26 @@ cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const i
                            float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
                            int32_t* ep_len, uint32_t* info_out, cudaStream_t stream) {
     bb_step_kernel<false><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, nullptr);
+        E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, nullptr, nullptr, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t bb_launch_step_range(const BBEnvArrays& E, const BBRewardCfg& cfg, int64_t off, int64_t cnt,
+                                 const int32_t* actions, float* rewards, uint8_t* terminated, uint64_t* mask_out,
+                                 int32_t* ep_score, int32_t* ep_len, uint32_t* info_out, uint64_t* board_out,
+                                 uint32_t* pieces_out, cudaStream_t stream) {
+    if (cnt <= 0) return cudaSuccess;
+    BBEnvArrays R = E;
+    R.s0 += off; R.s1 += off; R.s2 += off;
+    R.n = cnt;
+    R.env_offset += off;
+    if (R.ep_end) R.ep_end += off;
+    R.out_stride = E.n;
+#define BB_OFF(p) ((p) ? (p) + off : nullptr)
+    bb_step_kernel<false><<<bb_grid(cnt), BB_STEP_THREADS, 0, stream>>>(
+        R, cfg, actions + off, 1, 0, nullptr, BB_OFF(rewards), BB_OFF(terminated), BB_OFF(mask_out), BB_OFF(ep_score),
+        BB_OFF(ep_len), BB_OFF(info_out), nullptr, BB_OFF(board_out), BB_OFF(pieces_out));
+#undef BB_OFF
     return cudaGetLastError();
 }
 
@@ -422,7 +445,8 @@ cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, 
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
                                   uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream) {
     bb_step_kernel<true><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats);
+        E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats,
+        nullptr, nullptr);
     return cudaGetLastError();
 }
 

@@ -21,11 +21,18 @@ struct BBEnvArrays {
     uint64_t seed;
     uint32_t flags;
     BBEpisodeEnd* ep_end;   // optional [n] records written where an env terminates (bb_env_set_episode_end_buffer)
+    int64_t out_stride;     // plane stride of mask outputs; 0 = n (set when a launch covers a sub-range of the envs)
 };
 
 cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const int32_t* actions,
                            float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
                            int32_t* ep_len, uint32_t* info_out, cudaStream_t stream);
+// one step of envs [off, off + cnt) only (the host-buffer entry point pipelines chunks of the batch
+// against their device-to-host copies); output pointers are those of the WHOLE batch
+cudaError_t bb_launch_step_range(const BBEnvArrays& E, const BBRewardCfg& cfg, int64_t off, int64_t cnt,
+                                 const int32_t* actions, float* rewards, uint8_t* terminated, uint64_t* mask_out,
+                                 int32_t* ep_score, int32_t* ep_len, uint32_t* info_out, uint64_t* board_out,
+                                 uint32_t* pieces_out, cudaStream_t stream);
 cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps, int per_step,
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
                                   uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream);

@@ -236,14 +236,9 @@ class VectorizedBlockBlastEnv:
         if output == "numpy":
             pin = dict(pin_memory=True)
             self._h_actions = torch.zeros(n, dtype=torch.int32, **pin)
-            self._h_sets = [dict(rewards=torch.zeros(n, dtype=torch.float32, **pin),
-                                 term=torch.zeros(n, dtype=torch.uint8, **pin),
-                                 board=torch.zeros(n, dtype=torch.int64, **pin),
-                                 pieces=torch.zeros(n, dtype=torch.int32, **pin),
-                                 mask=torch.zeros((3, n), dtype=torch.int64, **pin),
-                                 ep_score=torch.zeros(n, dtype=torch.int32, **pin),
-                                 ep_len=torch.zeros(n, dtype=torch.int32, **pin),
-                                 info=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
+            # two result sets (double buffering), each ONE pinned block in the library's layout so a
+            # step's results arrive in a single transfer
+            self._h_sets = [capi.pinned_result_block(n) for _ in range(2)]
             self._h_flip = 0
         self._dones = np.zeros(n, dtype=bool)
         self._h_actions_np = self._h_actions.numpy() if output == "numpy" else None

@@ -138,7 +138,10 @@ int bb_env_set_state(bb_env* env, const void* host_records, void* stream);
 /* Same as bb_env_step but with HOST buffers (pinned memory recommended): copies actions to
  * the device, steps, copies rewards/terminated/packed obs back, synchronises.  This is the
  * call the numpy-facing VectorizedBlockBlastEnv.step makes.  board/pieces/mask/ep_* may be
- * NULL to skip that copy; h_info receives the per-env info word of bb_env_step. */
+ * NULL to skip that copy; h_info receives the per-env info word of bb_env_step.
+ * When all eight result arrays are given and sit in ONE host block at the offsets of
+ * bb_env_host_layout, they come back in a single 53 B/env transfer instead of eight. */
+int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes);
 int bb_env_step_host(bb_env* env, const int32_t* h_actions, float* h_rewards,
                      uint8_t* h_terminated, uint64_t* h_board, uint32_t* h_pieces,
                      uint64_t* h_mask, int32_t* h_ep_score, int32_t* h_ep_len, uint32_t* h_info,
