@@ -238,34 +238,79 @@ BB_HD int bb_holes(uint64_t b) {
 
 BB_HD int bb_center(uint64_t b) { return bb_popc(b & BB_CENTER); }
 
-// Line occupancy summary of a board: byte r of `rows` = filled cells of row r; nibble c of
-// `cols` = min(filled cells of column c, 15).  Used for "can a piece complete a line" bounds.
-struct BBLines { uint64_t rows; uint32_t cols; };
+// Line occupancy summary of a board: byte r of `rows` = filled cells of row r (0..8); `colp` =
+// the filled-cell counts of the eight columns in BIT-SLICED form: byte j holds, for every column
+// c (bit c), bit j of that column's count (a carry-save adder tree over the eight row bytes: 17
+// logic ops for all columns at once).  Used for "which lines can a piece complete" bounds.
+struct BBLines { uint64_t rows; uint32_t colp; };
+
+BB_HD uint32_t bb_maj(uint32_t x, uint32_t y, uint32_t z) { return (x & y) | (x & z) | (y & z); }
 
 BB_HD BBLines bb_lines(uint64_t b) {
     BBLines L;
     uint64_t t = b - ((b >> 1) & 0x5555555555555555ull);
     t = (t & 0x3333333333333333ull) + ((t >> 2) & 0x3333333333333333ull);
     L.rows = (t + (t >> 4)) & 0x0F0F0F0F0F0F0F0Full;
-    uint32_t cols = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // columns k and k+4 live in the low / high nibble of every byte
-        const uint64_t x = (b >> k) & 0x1111111111111111ull;
-        uint32_t s = (uint32_t)x + (uint32_t)(x >> 32);
-        s += s >> 16;
-        s += s >> 8;                // low byte: nibble0 = column k, nibble1 = column k+4
-        cols |= ((s & 0xFu) << (4 * k)) | (((s >> 4) & 0xFu) << (4 * (k + 4)));
-    }
-    L.cols = cols;
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    // rows k and k+4 -> 2-bit counts per byte lane
+    const uint32_t a1 = lo ^ hi, b1 = lo & hi;
+    // byte lanes k and k+2 -> 3-bit counts in lanes 0, 1
+    const uint32_t c = a1 & (a1 >> 16);
+    const uint32_t a2 = a1 ^ (a1 >> 16), b2 = b1 ^ (b1 >> 16) ^ c, d2 = bb_maj(b1, b1 >> 16, c);
+    // lanes 0 and 1 -> 4-bit counts in the low byte
+    const uint32_t c1 = a2 & (a2 >> 8);
+    const uint32_t ones = a2 ^ (a2 >> 8), twos = b2 ^ (b2 >> 8) ^ c1, c2 = bb_maj(b2, b2 >> 8, c1);
+    const uint32_t fours = d2 ^ (d2 >> 8) ^ c2, eights = bb_maj(d2, d2 >> 8, c2);
+    L.colp = (ones & 0xFFu) | ((twos & 0xFFu) << 8) | ((fours & 0xFFu) << 16) | ((eights & 0xFFu) << 24);
     return L;
+}
+// rows with at most m empty cells, as a byte mask (0xFF per such row), 1 <= m <= 7
+BB_HD uint64_t bb_rows_within_mask(const BBLines& L, int m) {
+    const uint64_t f = L.rows + (uint64_t)(0x78 + m) * BB_COL_A;   // bit 7 of a byte: count + 120 + m >= 128
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"((uint32_t)f), "r"(0u), "r"(0xBA98u));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"((uint32_t)(f >> 32)), "r"(0u), "r"(0xBA98u));
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+#else
+    return ((f & BB_COL_H) >> 7) * 0xFFull;
+#endif
+}
+// columns with at most m empty cells, as an 8-bit column mask: count + m >= 8 by a ripple carry
+// over the bit-sliced counts (1 <= m <= 7)
+BB_HD uint32_t bb_cols_within_bits(const BBLines& L, int m) {
+    const uint32_t ones = L.colp & 0xFFu, twos = (L.colp >> 8) & 0xFFu, fours = (L.colp >> 16) & 0xFFu, eights = L.colp >> 24;
+    const uint32_t m0 = 0u - ((uint32_t)m & 1u), m1 = 0u - (((uint32_t)m >> 1) & 1u), m2 = 0u - (((uint32_t)m >> 2) & 1u);
+    const uint32_t k0 = ones & m0;
+    const uint32_t k1 = bb_maj(twos, m1, k0);
+    const uint32_t k2 = bb_maj(fours, m2, k1);
+    return (eights | k2) & 0xFFu;
 }
 // exists a row with at most m empty cells / a column with at most m empty cells (1 <= m <= 7)
 BB_HD bool bb_row_within(const BBLines& L, int m) {
     return ((L.rows + (uint64_t)(0x78 + m) * BB_COL_A) & BB_COL_H) != 0;   // count + 120 + m >= 128
 }
-BB_HD bool bb_col_within(const BBLines& L, int m) {
-    return ((L.cols + (uint32_t)m * 0x11111111u) & 0x88888888u) != 0;       // count + m >= 8
+BB_HD bool bb_col_within(const BBLines& L, int m) { return bb_cols_within_bits(L, m) != 0u; }
+
+// Anchors of piece p whose placement covers at least one cell of T (the OR twin of bb_valid:
+// same recipe, OR instead of AND).  A superset is fine for its users, so wrapped bits are not
+// filtered here; the valid mask they are combined with removes out-of-bounds anchors.
+BB_HD uint64_t bb_cover(uint64_t T, const BBPiece& p) {
+    const uint32_t lo = (uint32_t)p.offs, hi = (uint32_t)(p.offs >> 32);
+    uint64_t v = bb_shr(T, bb_byte(lo, 0)) | bb_shr(T, bb_byte(lo, 1));
+    v |= bb_shr(T, bb_byte(lo, 2)) | bb_shr(T, lo >> 24);
+    v |= bb_shr(v, bb_byte(hi, 0));
+    v |= bb_shr(v, bb_byte(hi, 1));
+    return v;
+}
+
+// Anchors (a superset of those) at which placing p on board bb can complete a line: a completed
+// line has at most maxrow(p) (row) / maxcol(p) (column) empty cells and p covers all of them, in
+// particular one of them — so the anchor lies in the cover of the empty cells of such lines.
+BB_HD uint64_t bb_clearing_candidates(uint64_t bb, const BBLines& L, const BBPiece& p) {
+    const uint64_t near = bb_rows_within_mask(L, (int)BB_META_MAXROW(p.meta)) |
+                          ((uint64_t)bb_cols_within_bits(L, (int)BB_META_MAXCOL(p.meta)) * BB_COL_A);
+    return bb_cover(~bb & near, p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -456,8 +501,11 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
     // first placement cleared a line: everything about (A,B) is open; A first covers the
     // packings of both orders, B first matters only when B itself clears.  Nothing cleared:
     // a packing of (A,B) beside i is stage A's business, only clearing placements matter.
-    br.m0 = (full1 || bb_can_complete_line(L, br.A)) ? bb_valid(~br.bb, br.A) : 0ull;
-    br.m1 = bb_can_complete_line(L, br.B) ? bb_valid(~br.bb, br.B) : 0ull;
+    // second placements that cannot complete a line are dropped here (they used to be tested one
+    // by one in the unit loop): 4.2 -> 1.6 units per branch on boards from play
+    br.m0 = bb_valid(~br.bb, br.A);
+    if (!full1) br.m0 &= bb_clearing_candidates(br.bb, L, br.A);
+    br.m1 = bb_valid(~br.bb, br.B) & bb_clearing_candidates(br.bb, L, br.B);
     br.always = full1 ? 1u : 0u;
 }
 

@@ -105,3 +105,15 @@ int bbh_item_branch(uint64_t board, int p0, int p1, int p2, uint32_t t) {
 void bbh_work_reset() { memset(&g_bb_work, 0, sizeof(g_bb_work)); }
 
 }  // extern "C"
+
+// debug view of one opened branch (tools only): out = {bb, m0, m1, always, A.meta, B.meta, A.pm, B.pm}
+extern "C" void bbh_branch_info(uint64_t board, int p0, int p1, int p2, uint32_t t, uint64_t out[8]) {
+    init();
+    BBPiece P[3] = {bb_piece(&g_tables, (uint32_t)p0), bb_piece(&g_tables, (uint32_t)p1), bb_piece(&g_tables, (uint32_t)p2)};
+    BBItem it;
+    bb_classify(board, P[0], P[1], P[2], &it);
+    BBBranch br;
+    bb_branch_open(br, it, &g_tables, (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16), t);
+    out[0] = br.bb; out[1] = br.m0; out[2] = br.m1; out[3] = br.always; out[4] = br.A.meta; out[5] = br.B.meta;
+    out[6] = br.A.pm; out[7] = br.B.pm;
+}
