@@ -466,6 +466,25 @@ BB_HD bool bb_can_complete_line(const BBLines& L, const BBPiece& p) {
 
 #define BB_TRIO_ID(trio, i) (((trio) >> (8 * (i))) & 0xFFu)
 
+// "Always" phase shortcut: one placement of A overlaps at most n(A) * n(B) anchors of B, so when B
+// has more anchors than that, B fits beside ANY placement of A (a clear only makes more room):
+// one anchor of A is enough, its unit proves solvability.  This removes the long loops after a
+// clear has emptied the board (both pieces then have dozens of anchors).
+BB_HD uint64_t bb_one_anchor_if_roomy(uint64_t mA, uint64_t vB, const BBPiece& A, const BBPiece& B) {
+    const int roomy = bb_popc(vB) > (int)(BB_META_N(A.meta) * BB_META_N(B.meta));
+    return roomy ? (mA & (0ull - mA)) : mA;
+}
+
+// The "always" phase walks every anchor of A and asks whether B still fits; the roles are
+// symmetric (a packing is found from either side, and the other piece's own clearing placements
+// are phase 1's business), so walk the piece with FEWER anchors.
+BB_HD void bb_fewer_anchors_first(BBPiece& A, BBPiece& B, uint64_t& vA, uint64_t& vB) {
+    if (bb_popc(vB) < bb_popc(vA)) {
+        const BBPiece t = A; A = B; B = t;
+        const uint64_t v = vA; vA = vB; vB = v;
+    }
+}
+
 // open branch t of a HARD item, t in [0, nA + nB); pieces are fetched by role from the table
 BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uint32_t trio, uint32_t t) {
     BB_WORK(branches, 1);
@@ -480,7 +499,9 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
         br.B = bb_piece(T, BB_TRIO_ID(trio, z));
         BB_WORK(valid_calls, 2);
         // z must still fit beside x at all, else no packing goes through this anchor
-        br.m0 = bb_valid(~br.bb, br.B) ? bb_valid(~br.bb, br.A) : 0ull;
+        uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
+        bb_fewer_anchors_first(br.A, br.B, vA, vB);
+        br.m0 = vB ? bb_one_anchor_if_roomy(vA, vB, br.A, br.B) : 0ull;
         br.m1 = 0ull;
         br.always = 1u;
         return;
@@ -503,9 +524,14 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
     // a packing of (A,B) beside i is stage A's business, only clearing placements matter.
     // second placements that cannot complete a line are dropped here (they used to be tested one
     // by one in the unit loop): 4.2 -> 1.6 units per branch on boards from play
-    br.m0 = bb_valid(~br.bb, br.A);
-    if (!full1) br.m0 &= bb_clearing_candidates(br.bb, L, br.A);
-    br.m1 = bb_valid(~br.bb, br.B) & bb_clearing_candidates(br.bb, L, br.B);
+    uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
+    if (full1) {
+        bb_fewer_anchors_first(br.A, br.B, vA, vB);
+        br.m0 = bb_one_anchor_if_roomy(vA, vB, br.A, br.B);
+    } else {
+        br.m0 = vA & bb_clearing_candidates(br.bb, L, br.A);
+    }
+    br.m1 = vB & bb_clearing_candidates(br.bb, L, br.B);
     br.always = full1 ? 1u : 0u;
 }
 
