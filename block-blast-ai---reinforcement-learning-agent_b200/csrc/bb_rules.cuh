@@ -457,7 +457,7 @@ BB_HD int bb_classify(uint64_t b, const BBPiece& p0, const BBPiece& p1, const BB
 struct BBBranch {
     uint64_t bb, m0, m1;
     BBPiece A, B;
-    uint32_t always;   // bit 0: phase 0 always, bit 1: phase 1 always
+    uint32_t always;   // bit 0: phase 0 always, bit 1: phase 1 always, bit 2: roles of A and B swapped
 };
 
 BB_HD bool bb_can_complete_line(const BBLines& L, const BBPiece& p) {
@@ -475,16 +475,6 @@ BB_HD uint64_t bb_one_anchor_if_roomy(uint64_t mA, uint64_t vB, const BBPiece& A
     return roomy ? (mA & (0ull - mA)) : mA;
 }
 
-// The "always" phase walks every anchor of A and asks whether B still fits; the roles are
-// symmetric (a packing is found from either side, and the other piece's own clearing placements
-// are phase 1's business), so walk the piece with FEWER anchors.
-BB_HD void bb_fewer_anchors_first(BBPiece& A, BBPiece& B, uint64_t& vA, uint64_t& vB) {
-    if (bb_popc(vB) < bb_popc(vA)) {
-        const BBPiece t = A; A = B; B = t;
-        const uint64_t v = vA; vA = vB; vB = v;
-    }
-}
-
 // open branch t of a HARD item, t in [0, nA + nB); pieces are fetched by role from the table
 BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uint32_t trio, uint32_t t) {
     BB_WORK(branches, 1);
@@ -499,11 +489,14 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
         br.B = bb_piece(T, BB_TRIO_ID(trio, z));
         BB_WORK(valid_calls, 2);
         // z must still fit beside x at all, else no packing goes through this anchor
-        uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
-        bb_fewer_anchors_first(br.A, br.B, vA, vB);
-        br.m0 = vB ? bb_one_anchor_if_roomy(vA, vB, br.A, br.B) : 0ull;
+        const uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
+        // walk the piece with fewer anchors (roles are symmetric for a packing), one anchor of it
+        // when the other piece has more anchors than one placement can block
+        const bool flip = bb_popc(vB) < bb_popc(vA);
+        const uint64_t vf = flip ? vB : vA, vs = flip ? vA : vB;
+        br.m0 = vs ? bb_one_anchor_if_roomy(vf, vs, br.A, br.B) : 0ull;
         br.m1 = 0ull;
-        br.always = 1u;
+        br.always = 1u | (flip ? 4u : 0u);
         return;
     }
     int k = (int)(t - nA);
@@ -519,20 +512,18 @@ BB_HD void bb_branch_open(BBBranch& br, const BBItem& it, const BBTables* T, uin
     br.B = bb_piece(T, BB_TRIO_ID(trio, l));
     const BBLines L = bb_lines(br.bb);
     BB_WORK(valid_calls, 2);
-    // first placement cleared a line: everything about (A,B) is open; A first covers the
-    // packings of both orders, B first matters only when B itself clears.  Nothing cleared:
-    // a packing of (A,B) beside i is stage A's business, only clearing placements matter.
     // second placements that cannot complete a line are dropped here (they used to be tested one
     // by one in the unit loop): 4.2 -> 1.6 units per branch on boards from play
-    uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
-    if (full1) {
-        bb_fewer_anchors_first(br.A, br.B, vA, vB);
-        br.m0 = bb_one_anchor_if_roomy(vA, vB, br.A, br.B);
-    } else {
-        br.m0 = vA & bb_clearing_candidates(br.bb, L, br.A);
-    }
-    br.m1 = vB & bb_clearing_candidates(br.bb, L, br.B);
-    br.always = full1 ? 1u : 0u;
+    const uint64_t vA = bb_valid(~br.bb, br.A), vB = bb_valid(~br.bb, br.B);
+    const uint64_t cA = vA & bb_clearing_candidates(br.bb, L, br.A), cB = vB & bb_clearing_candidates(br.bb, L, br.B);
+    // first placement cleared a line: everything about the two other pieces is open — walk all
+    // anchors of one of them (the one with fewer; this covers the packings of both orders), the
+    // other one first only where it clears itself.  Nothing cleared: a packing beside i is stage
+    // A's business, only clearing second placements matter.
+    const bool flip = full1 && bb_popc(vB) < bb_popc(vA);
+    br.m0 = full1 ? bb_one_anchor_if_roomy(flip ? vB : vA, flip ? vA : vB, br.A, br.B) : cA;
+    br.m1 = flip ? cA : cB;
+    br.always = (full1 ? 1u : 0u) | (flip ? 4u : 0u);
 }
 
 // process one unit of an open branch (precondition: (m0 | m1) != 0); true = trio solvable
@@ -542,16 +533,18 @@ BB_HD bool bb_branch_unit(BBBranch& br) {
     const int a = bb_ctz(m);
     m &= m - 1;
     if (ph) br.m1 = m; else br.m0 = m;
+    // phase 0 places A and tests B, phase 1 the other way round; bit 2 of `always` swaps the roles
+    const bool useB = ph != (((br.always >> 2) & 1u) != 0u);
     bool full;
-    const uint64_t b2 = bb_clear_if_full(br.bb | ((ph ? br.B.pm : br.A.pm) << a), &full);
+    const uint64_t b2 = bb_clear_if_full(br.bb | ((useB ? br.B.pm : br.A.pm) << a), &full);
     BB_WORK(clear_iters, 1);
     if (!full && !((br.always >> (ph ? 1 : 0)) & 1u)) return false;
     BB_WORK(valid_calls, 1);
     BBPiece s2;
     s2.pm = 0;
-    s2.inb = ph ? br.A.inb : br.B.inb;
-    s2.offs = ph ? br.A.offs : br.B.offs;
-    s2.meta = ph ? br.A.meta : br.B.meta;
+    s2.inb = useB ? br.A.inb : br.B.inb;
+    s2.offs = useB ? br.A.offs : br.B.offs;
+    s2.meta = useB ? br.A.meta : br.B.meta;
     return bb_valid(~b2, s2) != 0ull;
 }
 
