@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 12.64e6 + 0.02e6   # measured by ncu for one 262,144-env launch (see traffic_source)
+NCU_DRAM_BYTES_PER_LAUNCH = 12.63e6 + 0.05e6   # measured by ncu for one 262,144-env launch (see traffic_source)
 ALGO_BYTES_PER_ENV_STEP = 129          # SURVEY.md §8d / DESIGN.md: 48 R + 48 W + 4 + 4 + 1 + 24
 STATE_BYTES, OUT_BYTES = 48, 33
 METRIC = "env_steps_per_sec"
@@ -573,10 +573,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                           "(profiles/r1_kernels_ncu_summary.json); reads are the 12.6 MB of state, the "
+                                           "(profiles/r1_k1_final_ncu_summary.txt); reads are the 12.6 MB of state, the "
                                            "21 MB of outputs + state write-back were still in the 126 MB L2 when the capture ended",
-                         "bound_note": "integer-issue bound, not HBM bound: ALU pipe ~50% busy over the launch, "
-                                       "32 M warp instructions, 17.5 of 32 lanes active per instruction (ncu)",
+                         "bound_note": "integer-issue bound, not HBM bound: ALU pipe 63% busy while an SM is active, SMs active 78% "
+                                       "of the launch, 28.9 M warp instructions, 21.9 of 32 lanes active per instruction (ncu)",
                          "kernel": "bb_step_kernel<true>",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
                          "launch_us": per_launch_s * 1e6},
