@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("BBGPU_LIB") or os.path.join(PKG_DIR, "libbbgpu.so")  
 BB_F32, BB_BF16, BB_U8 = 0, 1, 2
 ENV_RESEED_ON_RESET = 1
 ENV_NO_AUTO_RESET = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 REWARD_KEYS = ("line_clear_base", "block_placed", "game_over_penalty", "hole_penalty",
                "center_bonus", "combo_multiplier_bonus", "survival_bonus")
@@ -59,20 +59,27 @@ def lib():
     L.bb_env_num_envs.argtypes = [vp]
     L.bb_env_num_envs.restype = i64
     L.bb_env_set_episode_end_buffer.argtypes = [vp, vp]
+    L.bb_env_set_trios.argtypes = [vp, vp, i64, vp]
     L.bb_env_reset.argtypes = [vp, vp, vp, vp]
-    L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.bb_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bb_env_step_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.bb_env_rollout_random.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.bb_env_observe.argtypes = [vp, vp, vp, vp, vp]
     L.bb_env_sample_valid_actions.argtypes = [vp, u64, vp, vp, vp]
     L.bb_env_get_state.argtypes = [vp, vp, vp]
     L.bb_env_set_state.argtypes = [vp, vp, vp]
     L.bb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bb_env_fetch_step_info.argtypes = [vp, vp, vp, vp, vp]
+    L.bb_env_host_dense_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
+    L.bb_env_step_host_dense.argtypes = [vp, vp, vp, vp]
+    L.bb_env_observe_host_dense.argtypes = [vp, vp, vp]
     L.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
-    L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
+    L.bb_unpack_obs_reference_layout.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, vp]
+    L.bb_gather_minibatch.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, i64, vp, vp]
     L.bb_masked_head_backward.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, i64, vp]
     L.bb_ppo_loss.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, i64, vp]
-    L.bb_env_host_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
+    L.bb_env_host_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.bb_bn_workspace_size.restype = i64
     L.bb_bn_workspace_size.argtypes = [C.c_int]
     L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
@@ -149,16 +156,28 @@ class EnvHandle:
         self._ep_end_keepalive = records
         check(lib().bb_env_set_episode_end_buffer(self.h, ptr(records)))
 
+    def set_trios(self, trios):
+        """Injected candidate trios (replay / parity mode): uint8 array [n, L, 3] of piece indices,
+        or None to return to the Philox streams.  Call reset() afterwards."""
+        if trios is None:
+            check(lib().bb_env_set_trios(self.h, None, 0, current_stream()))
+            return
+        t = np.ascontiguousarray(trios, dtype=np.uint8)
+        assert t.ndim == 3 and t.shape[0] == self.n and t.shape[2] == 3, t.shape
+        check(lib().bb_env_set_trios(self.h, ptr(t), t.shape[1], current_stream()))
+
     def reset(self, reset_mask=None, mask_out=None):
         check(lib().bb_env_reset(self.h, ptr(reset_mask), ptr(mask_out), current_stream()))
 
-    def step(self, actions, rewards, terminated, mask_out=None, ep_score=None, ep_len=None, info_out=None):
-        check(lib().bb_env_step(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(mask_out),
-                                ptr(ep_score), ptr(ep_len), ptr(info_out), current_stream()))
+    def step(self, actions, rewards, terminated, mask_out=None, ep_score=None, ep_len=None, info_out=None,
+             board_out=None, pieces_out=None, stats=None):
+        check(lib().bb_env_step(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(mask_out), ptr(board_out),
+                                ptr(pieces_out), ptr(ep_score), ptr(ep_len), ptr(info_out), ptr(stats), current_stream()))
 
-    def step_random(self, n_steps=1, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
+    def step_random(self, n_steps=1, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None,
+                    mask_in=None):
         check(lib().bb_env_step_random(self.h, int(n_steps), ptr(actions_out), ptr(rewards), ptr(terminated),
-                                       ptr(mask_out), ptr(stats), current_stream()))
+                                       ptr(mask_out), ptr(stats), ptr(mask_in), current_stream()))
 
     def rollout_random(self, n_steps, actions_out=None, rewards=None, terminated=None, mask_out=None, stats=None):
         """n_steps in one launch, outputs of EVERY step written to [n_steps, ...] arrays."""
@@ -187,16 +206,49 @@ class EnvHandle:
         check(lib().bb_env_step_host(self.h, ptr(actions), ptr(rewards), ptr(terminated), ptr(board), ptr(pieces),
                                      ptr(mask), ptr(ep_score), ptr(ep_len), ptr(info), current_stream()))
 
+    def fetch_step_info(self, ep_score=None, ep_len=None, info=None):
+        """ep_score / ep_len / info arrays of the LAST host-buffer step (host buffers)."""
+        check(lib().bb_env_fetch_step_info(self.h, ptr(ep_score), ptr(ep_len), ptr(info), current_stream()))
+
+    def step_host_dense(self, actions, block):
+        """Host-buffer step returning the reference's dense observation layout in one pinned block."""
+        check(lib().bb_env_step_host_dense(self.h, ptr(actions), ptr(block), current_stream()))
+
+    def observe_host_dense(self, block):
+        check(lib().bb_env_observe_host_dense(self.h, ptr(block), current_stream()))
+
 
 HOST_LAYOUT_FIELDS = ("mask", "board", "rewards", "pieces", "ep_score", "ep_len", "info", "term")
 
 
 def host_layout(n_envs):
-    """({field: byte offset}, total bytes) of the single-block result layout of bb_env_step_host."""
+    """({field: byte offset}, total bytes) of the single-block result layout of bb_env_step_host
+    (mask/board/rewards/pieces/term form the per-step prefix, ep_score/ep_len/info the tail)."""
     offs = (C.c_int64 * 8)()
-    total = C.c_int64()
-    check(lib().bb_env_host_layout(int(n_envs), offs, C.byref(total)))
+    total, prefix = C.c_int64(), C.c_int64()
+    check(lib().bb_env_host_layout(int(n_envs), offs, C.byref(total), C.byref(prefix)))
     return dict(zip(HOST_LAYOUT_FIELDS, [int(o) for o in offs])), int(total.value)
+
+
+DENSE_LAYOUT_FIELDS = ("board", "pieces", "action_mask", "rewards", "term")
+
+
+def pinned_dense_block(n_envs):
+    """One pinned host block in the layout of bb_env_step_host_dense as typed torch views: board f32
+    [n,8,8], pieces f32 [n,3,8,8], action_mask int8 [n,192], rewards f32 [n], term u8 [n]."""
+    import torch
+    offs = (C.c_int64 * 5)()
+    total = C.c_int64()
+    n = int(n_envs)
+    check(lib().bb_env_host_dense_layout(n, offs, C.byref(total)))
+    block = torch.zeros(int(total.value), dtype=torch.uint8).pin_memory()
+    o = [int(x) for x in offs]
+    return {"_block": block,
+            "board": block[o[0]:o[1]].view(torch.float32).view(n, 8, 8),
+            "pieces": block[o[1]:o[2]].view(torch.float32).view(n, 3, 8, 8),
+            "action_mask": block[o[2]:o[3]].view(torch.int8).view(n, 192),
+            "rewards": block[o[3]:o[4]].view(torch.float32),
+            "term": block[o[4]:o[4] + n]}
 
 
 def pinned_result_block(n_envs):
@@ -225,14 +277,32 @@ def unpack_obs(board, pieces, mask, mask_stride, obs=None, mask_dense=None, n=No
                               ptr(mask_dense), mask_dt, n, current_stream()))
 
 
-def masked_sample(logits, mask, mask_stride, seed, call_counter, mode, action, logp=None, entropy=None):
+def unpack_obs_reference_layout(board, pieces, mask, mask_stride, board_f32, pieces_f32, action_mask_i8=None, n=None):
+    n = int(board.numel() if n is None else n)
+    check(lib().bb_unpack_obs_reference_layout(ptr(board), ptr(pieces), ptr(mask), int(mask_stride), ptr(board_f32),
+                                               ptr(pieces_f32), ptr(action_mask_i8), n, current_stream()))
+
+
+def gather_minibatch(index, n_envs, board, pieces, mask, action, logp, adv, ret, adv_mean_std, obs, mask_out,
+                     action_out, logp_out, adv_out, ret_out):
+    """RolloutBuffer.get_samples' gathers + K2 in one call (bb_gather_minibatch)."""
+    import torch
+    dt = BB_BF16 if obs.dtype == torch.bfloat16 else BB_F32
+    check(lib().bb_gather_minibatch(ptr(index), int(index.numel()), int(n_envs), ptr(board), ptr(pieces), ptr(mask),
+                                    ptr(action), ptr(logp), ptr(adv), ptr(ret), ptr(adv_mean_std), ptr(obs), dt,
+                                    ptr(mask_out), ptr(action_out), ptr(logp_out), ptr(adv_out), ptr(ret_out),
+                                    current_stream()))
+
+
+def masked_sample(logits, mask, mask_stride, seed, call_counter, mode, action, logp=None, entropy=None,
+                  row_offset=0, call_counter_dev=None):
     import torch
     n = logits.shape[0]
     assert logits.is_contiguous() and logits.shape[1] == 192
     dt = BB_BF16 if logits.dtype == torch.bfloat16 else BB_F32
     check(lib().bb_masked_sample(ptr(logits), dt, ptr(mask), int(mask_stride), int(seed) & (2 ** 64 - 1),
                                  int(call_counter), int(mode), ptr(action), ptr(logp), ptr(entropy), n,
-                                 current_stream()))
+                                 int(row_offset), ptr(call_counter_dev), current_stream()))
 
 
 def masked_head_backward(logits, mask, mask_stride, action, grad_logp, grad_entropy, grad_logits):

@@ -16,6 +16,10 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     return code;
 }
 #define BB_CUDA(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(-2, what, e__); } while (0)
+// every entry point that launches on an env's arrays runs with the env's device current
+#define BB_DEVICE(e, what) do { int d__ = -1; cudaError_t e__ = cudaGetDevice(&d__); \
+    if (e__ != cudaSuccess) return fail(-2, what, e__); \
+    if (d__ != (e)->device) return fail(-1, what ": the env lives on another CUDA device than the current one"); } while (0)
 
 struct bb_env {
     BBEnvArrays arr;
@@ -32,6 +36,8 @@ struct bb_env {
     int32_t* d_ep_len;
     uint32_t* d_info;
     uint8_t* d_block;      // the eight result arrays above live in this one allocation (bb_env_host_layout)
+    uint8_t* d_dense;      // lazily allocated reference-layout result block (bb_env_host_dense_layout)
+    uint8_t* d_trios;      // injected candidate trios (bb_env_set_trios), owned
 };
 
 static const double BB_DEFAULT_CFG[7] = {1.0, 0.01, -1.0, -0.05, 0.02, 0.5, 0.001};
@@ -39,6 +45,7 @@ static const double BB_DEFAULT_CFG[7] = {1.0, 0.01, -1.0, -0.05, 0.02, 0.5, 0.00
 extern "C" {
 
 static int ensure_staging(bb_env* e);
+static int ensure_dense(bb_env* e);
 
 int bb_version(void) { return BB_ABI_VERSION; }
 const char* bb_last_error(void) { return g_err; }
@@ -61,25 +68,31 @@ int bb_env_create(bb_env** out, int64_t n_envs, uint64_t seed, int64_t global_en
     bb_env* e = new (std::nothrow) bb_env();
     if (!e) return fail(-3, "bb_env_create: out of host memory");
     memset(e, 0, sizeof(*e));
-    BB_CUDA(cudaGetDevice(&e->device), "cudaGetDevice");
+    cudaError_t err = cudaGetDevice(&e->device);
+    if (err != cudaSuccess) {
+        bb_env_destroy(e);
+        return fail(-2, "bb_env_create: cudaGetDevice", err);
+    }
     e->arr.n = n_envs;
     e->arr.env_offset = global_env_offset;
+    e->arr.trio_base = global_env_offset;
     e->arr.seed = seed;
     e->arr.flags = flags;
     const double* c = reward_cfg ? reward_cfg : BB_DEFAULT_CFG;
     e->cfg.line_clear_base = c[0]; e->cfg.block_placed = c[1]; e->cfg.game_over_penalty = c[2];
     e->cfg.hole_penalty = c[3]; e->cfg.center_bonus = c[4]; e->cfg.combo_multiplier_bonus = c[5];
     e->cfg.survival_bonus = c[6];
-    cudaError_t err;
     const size_t bytes = (size_t)n_envs * sizeof(uint4);
     if ((err = cudaMalloc(&e->arr.s0, bytes)) != cudaSuccess || (err = cudaMalloc(&e->arr.s1, bytes)) != cudaSuccess ||
         (err = cudaMalloc(&e->arr.s2, bytes)) != cudaSuccess) {
         bb_env_destroy(e);
         return fail(-2, "bb_env_create: cudaMalloc state", err);
     }
-    cudaMemset(e->arr.s0, 0, bytes);
-    cudaMemset(e->arr.s1, 0, bytes);
-    cudaMemset(e->arr.s2, 0, bytes);
+    if ((err = cudaMemset(e->arr.s0, 0, bytes)) != cudaSuccess || (err = cudaMemset(e->arr.s1, 0, bytes)) != cudaSuccess ||
+        (err = cudaMemset(e->arr.s2, 0, bytes)) != cudaSuccess) {
+        bb_env_destroy(e);
+        return fail(-2, "bb_env_create: cudaMemset state", err);
+    }
     // the first reset (the reference constructs each GameEngine with a dealt trio)
     err = bb_launch_reset(e->arr, nullptr, nullptr, 0);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
@@ -94,7 +107,7 @@ int bb_env_create(bb_env** out, int64_t n_envs, uint64_t seed, int64_t global_en
 int bb_env_destroy(bb_env* e) {
     if (!e) return 0;
     cudaFree(e->arr.s0); cudaFree(e->arr.s1); cudaFree(e->arr.s2);
-    cudaFree(e->d_actions); cudaFree(e->d_block);
+    cudaFree(e->d_actions); cudaFree(e->d_block); cudaFree(e->d_dense); cudaFree(e->d_trios);
     delete e;
     return 0;
 }
@@ -107,41 +120,72 @@ int bb_env_set_episode_end_buffer(bb_env* e, void* records) {
     return 0;
 }
 
+int bb_env_set_trios(bb_env* e, const uint8_t* h_trios, int64_t len, void* stream) {
+    if (!e) return fail(-1, "bb_env_set_trios: env is NULL");
+    BB_DEVICE(e, "bb_env_set_trios");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h_trios) {                      // back to the Philox streams
+        BB_CUDA(cudaStreamSynchronize(s), "bb_env_set_trios sync");
+        cudaFree(e->d_trios);
+        e->d_trios = nullptr; e->arr.trios = nullptr; e->arr.trio_len = 0;
+        return 0;
+    }
+    if (len <= 0) return fail(-1, "bb_env_set_trios: len must be > 0");
+    const size_t bytes = (size_t)e->arr.n * (size_t)len * 3;
+    for (size_t k = 0; k < bytes; ++k)
+        if (h_trios[k] >= BB_NUM_PIECES) return fail(-1, "bb_env_set_trios: piece index out of range");
+    uint8_t* d = nullptr;
+    BB_CUDA(cudaMalloc(&d, bytes), "bb_env_set_trios: cudaMalloc");
+    cudaError_t err = cudaMemcpyAsync(d, h_trios, bytes, cudaMemcpyHostToDevice, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) { cudaFree(d); return fail(-2, "bb_env_set_trios: copy", err); }
+    cudaFree(e->d_trios);
+    e->d_trios = d; e->arr.trios = d; e->arr.trio_len = len;
+    BB_CUDA(bb_launch_zero_draw_ctr(e->arr, s), "bb_env_set_trios: draw counters");
+    return 0;
+}
+
 int bb_env_reset(bb_env* e, const uint8_t* reset_mask, uint64_t* mask_out, void* stream) {
     if (!e) return fail(-1, "bb_env_reset: env is NULL");
+    BB_DEVICE(e, "bb_env_reset");
     BB_CUDA(bb_launch_reset(e->arr, reset_mask, mask_out, (cudaStream_t)stream), "bb_env_reset launch");
     return 0;
 }
 
 int bb_env_step(bb_env* e, const int32_t* actions, float* rewards, uint8_t* terminated,
-                uint64_t* mask_out, int32_t* ep_score, int32_t* ep_len, uint32_t* info_out, void* stream) {
+                uint64_t* mask_out, uint64_t* board_out, uint32_t* pieces_out, int32_t* ep_score, int32_t* ep_len,
+                uint32_t* info_out, uint64_t* stats, void* stream) {
     if (!e) return fail(-1, "bb_env_step: env is NULL");
     if (!actions || !rewards || !terminated) return fail(-1, "bb_env_step: actions/rewards/terminated are required");
-    BB_CUDA(bb_launch_step(e->arr, e->cfg, actions, rewards, terminated, mask_out, ep_score, ep_len, info_out,
-                           (cudaStream_t)stream), "bb_env_step launch");
+    BB_DEVICE(e, "bb_env_step");
+    BB_CUDA(bb_launch_step(e->arr, e->cfg, actions, rewards, terminated, mask_out, board_out, pieces_out, ep_score, ep_len,
+                           info_out, (unsigned long long*)stats, (cudaStream_t)stream), "bb_env_step launch");
     return 0;
 }
 
 int bb_env_step_random(bb_env* e, int32_t n_steps, int32_t* actions_out, float* rewards, uint8_t* terminated,
-                       uint64_t* mask_out, uint64_t* stats, void* stream) {
+                       uint64_t* mask_out, uint64_t* stats, const uint64_t* mask_in, void* stream) {
     if (!e) return fail(-1, "bb_env_step_random: env is NULL");
-    if (n_steps < 1) return fail(-1, "bb_env_step_random: n_steps must be >= 1");
+    if (n_steps < 1 || n_steps > (1 << 20)) return fail(-1, "bb_env_step_random: n_steps must be in [1, 2^20]");
+    BB_DEVICE(e, "bb_env_step_random");
     BB_CUDA(bb_launch_step_random(e->arr, e->cfg, n_steps, 0, actions_out, rewards, terminated, mask_out,
-                                  (unsigned long long*)stats, (cudaStream_t)stream), "bb_env_step_random launch");
+                                  (unsigned long long*)stats, mask_in, (cudaStream_t)stream), "bb_env_step_random launch");
     return 0;
 }
 
 int bb_env_rollout_random(bb_env* e, int32_t n_steps, int32_t* actions_out, float* rewards, uint8_t* terminated,
                           uint64_t* mask_out, uint64_t* stats, void* stream) {
     if (!e) return fail(-1, "bb_env_rollout_random: env is NULL");
-    if (n_steps < 1) return fail(-1, "bb_env_rollout_random: n_steps must be >= 1");
+    if (n_steps < 1 || n_steps > (1 << 20)) return fail(-1, "bb_env_rollout_random: n_steps must be in [1, 2^20]");
+    BB_DEVICE(e, "bb_env_rollout_random");
     BB_CUDA(bb_launch_step_random(e->arr, e->cfg, n_steps, 1, actions_out, rewards, terminated, mask_out,
-                                  (unsigned long long*)stats, (cudaStream_t)stream), "bb_env_rollout_random launch");
+                                  (unsigned long long*)stats, nullptr, (cudaStream_t)stream), "bb_env_rollout_random launch");
     return 0;
 }
 
 int bb_env_observe(bb_env* e, uint64_t* board_out, uint32_t* pieces_out, uint64_t* mask_out, void* stream) {
     if (!e) return fail(-1, "bb_env_observe: env is NULL");
+    BB_DEVICE(e, "bb_env_observe");
     BB_CUDA(bb_launch_observe(e->arr, board_out, pieces_out, mask_out, (cudaStream_t)stream), "bb_env_observe launch");
     return 0;
 }
@@ -149,6 +193,7 @@ int bb_env_observe(bb_env* e, uint64_t* board_out, uint32_t* pieces_out, uint64_
 int bb_env_sample_valid_actions(bb_env* e, uint64_t call_counter, int32_t* actions_out, int32_t* h_actions_out, void* stream) {
     if (!e) return fail(-1, "bb_env_sample_valid_actions: env is NULL");
     if (!actions_out && !h_actions_out) return fail(-1, "bb_env_sample_valid_actions: no output given");
+    BB_DEVICE(e, "bb_env_sample_valid_actions");
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* d = actions_out;
     if (!d) {
@@ -165,6 +210,7 @@ int bb_env_sample_valid_actions(bb_env* e, uint64_t call_counter, int32_t* actio
 
 int bb_env_get_state(bb_env* e, void* host_records, void* stream) {
     if (!e || !host_records) return fail(-1, "bb_env_get_state: NULL argument");
+    BB_DEVICE(e, "bb_env_get_state");
     const int64_t n = e->arr.n;
     uint4* tmp = (uint4*)malloc((size_t)n * 3 * sizeof(uint4));
     if (!tmp) return fail(-3, "bb_env_get_state: out of host memory");
@@ -182,6 +228,7 @@ int bb_env_get_state(bb_env* e, void* host_records, void* stream) {
 
 int bb_env_set_state(bb_env* e, const void* host_records, void* stream) {
     if (!e || !host_records) return fail(-1, "bb_env_set_state: NULL argument");
+    BB_DEVICE(e, "bb_env_set_state");
     const int64_t n = e->arr.n;
     uint4* tmp = (uint4*)malloc((size_t)n * 3 * sizeof(uint4));
     if (!tmp) return fail(-3, "bb_env_set_state: out of host memory");
@@ -205,27 +252,38 @@ int bb_env_set_state(bb_env* e, const void* host_records, void* stream) {
 }
 
 // Result arrays of the host-buffer step, as byte offsets into ONE block of `total` bytes:
-// [0] mask u64[3][n], [1] board u64[n], [2] rewards f32[n], [3] pieces u32[n], [4] ep_score i32[n],
-// [5] ep_len i32[n], [6] info u32[n], [7] terminated u8[n].  A caller whose eight host arrays sit
-// in one pinned block at these offsets gets them with a single device-to-host copy.
-int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes) {
+// [0] mask u64[3][n], [1] board u64[n], [2] rewards f32[n], [3] pieces u32[n], [7] terminated u8[n] form
+// the PREFIX (41 B/env, rounded up to 16) every step needs; [4] ep_score i32[n], [5] ep_len i32[n],
+// [6] info u32[n] follow it.  A caller whose host arrays sit in one pinned block at these offsets gets
+// the prefix (or, when it also passes the three tail arrays, the whole block) in ONE device-to-host
+// copy; the tail of the last step can be fetched later with bb_env_fetch_step_info.
+int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes, int64_t* prefix_bytes) {
     if (n_envs <= 0 || !offsets8 || !total_bytes) return fail(-1, "bb_env_host_layout: bad argument");
     const int64_t n = n_envs;
-    offsets8[0] = 0; offsets8[1] = 24 * n; offsets8[2] = 32 * n; offsets8[3] = 36 * n; offsets8[4] = 40 * n;
-    offsets8[5] = 44 * n; offsets8[6] = 48 * n; offsets8[7] = 52 * n;
-    *total_bytes = 53 * n;
+    const int64_t prefix = (41 * n + 15) / 16 * 16;
+    offsets8[0] = 0; offsets8[1] = 24 * n; offsets8[2] = 32 * n; offsets8[3] = 36 * n; offsets8[7] = 40 * n;
+    offsets8[4] = prefix; offsets8[5] = prefix + 4 * n; offsets8[6] = prefix + 8 * n;
+    *total_bytes = prefix + 12 * n;
+    if (prefix_bytes) *prefix_bytes = prefix;
     return 0;
 }
 
 static int ensure_staging(bb_env* e) {
-    if (e->d_actions) return 0;
+    if (e->d_block) return 0;
     const int64_t n = e->arr.n;
     int64_t off[8], total;
-    bb_env_host_layout(n, off, &total);
-    cudaError_t err = cudaMalloc(&e->d_actions, n * sizeof(int32_t));
-    if (err == cudaSuccess) err = cudaMalloc(&e->d_block, (size_t)total);
-    if (err != cudaSuccess) return fail(-2, "bb_env_step_host: cudaMalloc staging", err);
-    cudaMemset(e->d_block, 0, (size_t)total);
+    bb_env_host_layout(n, off, &total, nullptr);
+    int32_t* da = nullptr;
+    uint8_t* db = nullptr;
+    cudaError_t err = cudaMalloc(&da, n * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&db, (size_t)total);
+    if (err == cudaSuccess) err = cudaMemset(db, 0, (size_t)total);
+    if (err != cudaSuccess) {
+        cudaFree(da); cudaFree(db);
+        return fail(-2, "bb_env_step_host: staging buffers", err);
+    }
+    e->d_actions = da;
+    e->d_block = db;
     e->d_mask = (uint64_t*)(e->d_block + off[0]);
     e->d_board = (uint64_t*)(e->d_block + off[1]);
     e->d_rewards = (float*)(e->d_block + off[2]);
@@ -242,25 +300,28 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
                      int32_t* h_ep_len, uint32_t* h_info, void* stream) {
     if (!e) return fail(-1, "bb_env_step_host: env is NULL");
     if (!h_actions || !h_rewards || !h_terminated) return fail(-1, "bb_env_step_host: actions/rewards/terminated are required");
+    BB_DEVICE(e, "bb_env_step_host");
     if (int rc = ensure_staging(e)) return rc;
     const int64_t n = e->arr.n;
     cudaStream_t s = (cudaStream_t)stream;
     BB_CUDA(cudaMemcpyAsync(e->d_actions, h_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s), "H2D actions");
-    // the step kernel writes the packed next observation (board, pieces) itself
+    // the step kernel writes the packed next observation (board, pieces) itself; the per-step info
+    // arrays always land in the device staging block (bb_env_fetch_step_info reads them later)
     BB_CUDA(bb_launch_step_range(e->arr, e->cfg, 0, n, e->d_actions, e->d_rewards, e->d_terminated,
-                                 h_mask ? e->d_mask : nullptr, h_ep_score ? e->d_ep_score : nullptr,
-                                 h_ep_len ? e->d_ep_len : nullptr, h_info ? e->d_info : nullptr,
-                                 h_board ? e->d_board : nullptr, h_pieces ? e->d_pieces : nullptr, s),
+                                 e->d_mask, e->d_ep_score, e->d_ep_len, e->d_info, e->d_board, e->d_pieces, s),
             "bb_env_step_host launch");
-    int64_t off[8], total;
-    bb_env_host_layout(n, off, &total);
+    int64_t off[8], total, prefix;
+    bb_env_host_layout(n, off, &total, &prefix);
     uint8_t* hb = (uint8_t*)h_mask;
-    const bool one_block = hb && (uint8_t*)h_board == hb + off[1] && (uint8_t*)h_rewards == hb + off[2] &&
-                           (uint8_t*)h_pieces == hb + off[3] && (uint8_t*)h_ep_score == hb + off[4] &&
-                           (uint8_t*)h_ep_len == hb + off[5] && (uint8_t*)h_info == hb + off[6] && h_terminated == hb + off[7];
-    if (one_block) {
-        // one 53 B/env transfer instead of eight calls (each costs several microseconds of driver time)
-        BB_CUDA(cudaMemcpyAsync(hb, e->d_block, (size_t)total, cudaMemcpyDeviceToHost, s), "D2H results");
+    const bool prefix_block = hb && (uint8_t*)h_board == hb + off[1] && (uint8_t*)h_rewards == hb + off[2] &&
+                              (uint8_t*)h_pieces == hb + off[3] && h_terminated == hb + off[7];
+    const bool tail_block = (uint8_t*)h_ep_score == hb + off[4] && (uint8_t*)h_ep_len == hb + off[5] &&
+                            (uint8_t*)h_info == hb + off[6];
+    const bool no_tail = !h_ep_score && !h_ep_len && !h_info;
+    if (prefix_block && (tail_block || no_tail)) {
+        // one transfer (41 B/env, or 53 B/env with the info tail) instead of up to eight calls, each of
+        // which costs several microseconds of driver time
+        BB_CUDA(cudaMemcpyAsync(hb, e->d_block, (size_t)(tail_block ? total : 41 * n), cudaMemcpyDeviceToHost, s), "D2H results");
     } else {
         BB_CUDA(cudaMemcpyAsync(h_rewards, e->d_rewards, n * sizeof(float), cudaMemcpyDeviceToHost, s), "D2H rewards");
         BB_CUDA(cudaMemcpyAsync(h_terminated, e->d_terminated, n, cudaMemcpyDeviceToHost, s), "D2H terminated");
@@ -275,6 +336,87 @@ int bb_env_step_host(bb_env* e, const int32_t* h_actions, float* h_rewards, uint
     return 0;
 }
 
+int bb_env_fetch_step_info(bb_env* e, int32_t* h_ep_score, int32_t* h_ep_len, uint32_t* h_info, void* stream) {
+    if (!e) return fail(-1, "bb_env_fetch_step_info: env is NULL");
+    BB_DEVICE(e, "bb_env_fetch_step_info");
+    if (!e->d_block) return fail(-1, "bb_env_fetch_step_info: no host-buffer step has run yet");
+    const int64_t n = e->arr.n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h_ep_score && h_ep_len && h_info && (uint8_t*)h_ep_len == (uint8_t*)h_ep_score + 4 * n &&
+        (uint8_t*)h_info == (uint8_t*)h_ep_score + 8 * n) {
+        BB_CUDA(cudaMemcpyAsync(h_ep_score, e->d_ep_score, 12 * n, cudaMemcpyDeviceToHost, s), "D2H step info");
+    } else {
+        if (h_ep_score) BB_CUDA(cudaMemcpyAsync(h_ep_score, e->d_ep_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_score");
+        if (h_ep_len) BB_CUDA(cudaMemcpyAsync(h_ep_len, e->d_ep_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H ep_len");
+        if (h_info) BB_CUDA(cudaMemcpyAsync(h_info, e->d_info, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "D2H info");
+    }
+    BB_CUDA(cudaStreamSynchronize(s), "bb_env_fetch_step_info sync");
+    return 0;
+}
+
+// Reference-layout ("dense") result block: [0] board f32[n][8][8], [1] pieces f32[n][3][8][8],
+// [2] action_mask i8[n][192], [3] rewards f32[n], [4] terminated u8[n]  = 1,221 B/env.
+int bb_env_host_dense_layout(int64_t n_envs, int64_t offsets5[5], int64_t* total_bytes) {
+    if (n_envs <= 0 || !offsets5 || !total_bytes) return fail(-1, "bb_env_host_dense_layout: bad argument");
+    const int64_t n = n_envs;
+    offsets5[0] = 0; offsets5[1] = 256 * n; offsets5[2] = 1024 * n; offsets5[3] = 1216 * n; offsets5[4] = 1220 * n;
+    *total_bytes = 1221 * n;
+    return 0;
+}
+
+static int ensure_dense(bb_env* e) {
+    if (e->d_dense) return 0;
+    int64_t off[5], total;
+    bb_env_host_dense_layout(e->arr.n, off, &total);
+    uint8_t* d = nullptr;
+    cudaError_t err = cudaMalloc(&d, (size_t)total);
+    if (err == cudaSuccess) err = cudaMemset(d, 0, (size_t)total);
+    if (err != cudaSuccess) { cudaFree(d); return fail(-2, "bb_env_step_host_dense: staging buffer", err); }
+    e->d_dense = d;
+    return 0;
+}
+
+// expand the packed observation in the staging block into the dense block and bring it to the host
+static int dense_to_host(bb_env* e, void* h_block, cudaStream_t s) {
+    const int64_t n = e->arr.n;
+    int64_t off[5], total;
+    bb_env_host_dense_layout(n, off, &total);
+    BB_CUDA(bb_launch_unpack_obs(e->d_board, e->d_pieces, e->d_mask, n, e->d_dense + off[0], BB_F32, e->d_dense + off[2],
+                                 BB_U8, n, s, e->d_dense + off[1]), "dense observation expand");
+    BB_CUDA(cudaMemcpyAsync(h_block, e->d_dense, (size_t)total, cudaMemcpyDeviceToHost, s), "D2H dense results");
+    BB_CUDA(cudaStreamSynchronize(s), "dense results sync");
+    return 0;
+}
+
+int bb_env_step_host_dense(bb_env* e, const int32_t* h_actions, void* h_block, void* stream) {
+    if (!e) return fail(-1, "bb_env_step_host_dense: env is NULL");
+    if (!h_actions || !h_block) return fail(-1, "bb_env_step_host_dense: actions and the result block are required");
+    BB_DEVICE(e, "bb_env_step_host_dense");
+    if (int rc = ensure_staging(e)) return rc;
+    if (int rc = ensure_dense(e)) return rc;
+    const int64_t n = e->arr.n;
+    int64_t off[5], total;
+    bb_env_host_dense_layout(n, off, &total);
+    cudaStream_t s = (cudaStream_t)stream;
+    BB_CUDA(cudaMemcpyAsync(e->d_actions, h_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s), "H2D actions");
+    // rewards / terminated go straight into the dense block, the packed observation into the staging block
+    BB_CUDA(bb_launch_step_range(e->arr, e->cfg, 0, n, e->d_actions, (float*)(e->d_dense + off[3]), e->d_dense + off[4],
+                                 e->d_mask, e->d_ep_score, e->d_ep_len, e->d_info, e->d_board, e->d_pieces, s),
+            "bb_env_step_host_dense launch");
+    return dense_to_host(e, h_block, s);
+}
+
+int bb_env_observe_host_dense(bb_env* e, void* h_block, void* stream) {
+    if (!e) return fail(-1, "bb_env_observe_host_dense: env is NULL");
+    if (!h_block) return fail(-1, "bb_env_observe_host_dense: the result block is required");
+    BB_DEVICE(e, "bb_env_observe_host_dense");
+    if (int rc = ensure_staging(e)) return rc;
+    if (int rc = ensure_dense(e)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    BB_CUDA(bb_launch_observe(e->arr, e->d_board, e->d_pieces, e->d_mask, s), "bb_env_observe_host_dense launch");
+    return dense_to_host(e, h_block, s);
+}
+
 int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask, int64_t mask_stride,
                   void* obs_nchw, int obs_dtype, void* mask_dense, int mask_dtype, int64_t n, void* stream) {
     if (n < 0) return fail(-1, "bb_unpack_obs: negative n");
@@ -282,26 +424,49 @@ int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t*
     if (mask_dense && mask_dtype != BB_F32 && mask_dtype != BB_U8) return fail(-1, "bb_unpack_obs: mask_dtype must be BB_F32 or BB_U8");
     if (n == 0) return 0;
     if (obs_nchw && (!board || !pieces)) return fail(-1, "bb_unpack_obs: board/pieces required for obs");
-    if (obs_nchw && obs_dtype != BB_F32 && obs_dtype != BB_BF16) return fail(-1, "bb_unpack_obs: obs_dtype must be BB_F32 or BB_BF16");
     if (mask_dense && !mask) return fail(-1, "bb_unpack_obs: mask required for mask_dense");
-    if (mask_dense && mask_dtype != BB_F32 && mask_dtype != BB_U8) return fail(-1, "bb_unpack_obs: mask_dtype must be BB_F32 or BB_U8");
     BB_CUDA(bb_launch_unpack_obs(board, pieces, mask, mask_stride, obs_nchw, obs_dtype, mask_dense, mask_dtype, n,
                                  (cudaStream_t)stream), "bb_unpack_obs launch");
     return 0;
 }
 
+int bb_unpack_obs_reference_layout(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask, int64_t mask_stride,
+                                   float* board_f32, float* pieces_f32, int8_t* action_mask_i8, int64_t n, void* stream) {
+    if (n < 0) return fail(-1, "bb_unpack_obs_reference_layout: negative n");
+    if (n == 0) return 0;
+    if (!board || !pieces || !board_f32 || !pieces_f32) return fail(-1, "bb_unpack_obs_reference_layout: board/pieces arrays are required");
+    if (action_mask_i8 && !mask) return fail(-1, "bb_unpack_obs_reference_layout: mask required for action_mask");
+    BB_CUDA(bb_launch_unpack_obs(board, pieces, mask, mask_stride, board_f32, BB_F32, action_mask_i8, BB_U8, n,
+                                 (cudaStream_t)stream, pieces_f32), "bb_unpack_obs_reference_layout launch");
+    return 0;
+}
+
+int bb_gather_minibatch(const int64_t* index, int64_t batch, int64_t n_envs, const uint64_t* board, const uint32_t* pieces,
+                        const uint64_t* mask, const int32_t* action, const float* logp, const float* adv, const float* ret,
+                        const float* adv_mean_std, void* obs_nchw, int obs_dtype, uint64_t* mask_out, int32_t* action_out,
+                        float* logp_out, float* adv_out, float* ret_out, void* stream) {
+    if (batch < 0 || n_envs <= 0) return fail(-1, "bb_gather_minibatch: bad size");
+    if (obs_dtype != BB_F32 && obs_dtype != BB_BF16) return fail(-1, "bb_gather_minibatch: obs_dtype must be BB_F32 or BB_BF16");
+    if (batch == 0) return 0;
+    if (!index || !board || !pieces || !mask || !action || !logp || !adv || !ret || !obs_nchw || !mask_out || !action_out ||
+        !logp_out || !adv_out || !ret_out)
+        return fail(-1, "bb_gather_minibatch: NULL array");
+    BB_CUDA(bb_launch_gather_minibatch(index, batch, n_envs, board, pieces, mask, action, logp, adv, ret, adv_mean_std,
+                                       obs_nchw, obs_dtype, mask_out, action_out, logp_out, adv_out, ret_out,
+                                       (cudaStream_t)stream), "bb_gather_minibatch launch");
+    return 0;
+}
+
 int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask, int64_t mask_stride,
                      uint64_t seed, uint64_t call_counter, int mode, int32_t* action, float* logp,
-                     float* entropy, int64_t n, void* stream) {
+                     float* entropy, int64_t n, int64_t row_offset, const uint64_t* call_counter_dev, void* stream) {
     if (n < 0) return fail(-1, "bb_masked_sample: negative n");
     if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_masked_sample: logits_dtype must be BB_F32 or BB_BF16");
     if (mode < 0 || mode > 2) return fail(-1, "bb_masked_sample: mode must be 0, 1 or 2");
     if (n == 0) return 0;
     if (!logits || !mask || !action) return fail(-1, "bb_masked_sample: logits/mask/action are required");
-    if (logits_dtype != BB_F32 && logits_dtype != BB_BF16) return fail(-1, "bb_masked_sample: logits_dtype must be BB_F32 or BB_BF16");
-    if (mode < 0 || mode > 2) return fail(-1, "bb_masked_sample: mode must be 0, 1 or 2");
     BB_CUDA(bb_launch_masked_sample(logits, logits_dtype, mask, mask_stride, seed, call_counter, mode, action, logp,
-                                    entropy, n, (cudaStream_t)stream), "bb_masked_sample launch");
+                                    entropy, n, (cudaStream_t)stream, row_offset, call_counter_dev), "bb_masked_sample launch");
     return 0;
 }
 

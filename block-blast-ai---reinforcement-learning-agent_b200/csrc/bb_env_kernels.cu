@@ -154,7 +154,7 @@ __device__ __forceinline__ bool bb_warp_solve(bool hard, const BBItem& item, uin
 }
 
 __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, const BBTables* T,
-                                                 uint64_t seed, uint64_t env_id, uint32_t& pieces,
+                                                 const BBTrioSrc& src, uint64_t env_id, uint32_t& pieces,
                                                  uint32_t& draw_ctr, BBProf& pf) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -180,7 +180,7 @@ __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, c
         uint32_t trio = 0;
         int cls = BB_REJECT;
         if (cand) {
-            trio = bb_draw_trio(seed, oid, octr + (uint32_t)r);
+            trio = bb_candidate(src, oid, octr + (uint32_t)r);
             cls = bb_classify(ob, bb_piece(T, trio & 0xFFu), bb_piece(T, (trio >> 8) & 0xFFu),
                               bb_piece(T, (trio >> 16) & 0xFFu), &item);
         }
@@ -219,26 +219,40 @@ __device__ __forceinline__ uint32_t bb_warp_deal(bool pending, uint64_t board, c
 // K1: one env step per thread; RANDOM fuses the uniform-random-valid policy and may run
 // n_steps back to back with the state held in registers.
 // ---------------------------------------------------------------------------------------
-template <bool RANDOM>
+// INJECT: candidate trios come from the table of bb_env_set_trios (replay / parity runs) instead of
+// Philox; a template parameter so that the production kernels do not carry the table pointer.
+template <bool RANDOM, bool INJECT>
 __global__ void __launch_bounds__(BB_STEP_THREADS, BB_STEP_MIN_BLOCKS)
 bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actions, int n_steps, int per_step,
                int32_t* __restrict__ actions_out, float* __restrict__ rewards,
                uint8_t* __restrict__ terminated, uint64_t* __restrict__ mask_out,
                int32_t* __restrict__ ep_score, int32_t* __restrict__ ep_len,
                uint32_t* __restrict__ info_out, unsigned long long* __restrict__ stats,
-               uint64_t* __restrict__ board_out, uint32_t* __restrict__ pieces_out) {
+               uint64_t* __restrict__ board_out, uint32_t* __restrict__ pieces_out,
+               const uint64_t* __restrict__ mask_in) {
     const BBTables& T = g_bb_tables;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < E.n;
-    unsigned long long st_eps = 0, st_score = 0, st_len = 0;
+    unsigned st_eps = 0, st_score = 0, st_len = 0, st_max = 0;   // per thread, 32 bits: n_steps <= 2^20 (API check)
+    BBTrioSrc src(E.seed);
+    if (INJECT) { src.trios = E.trios; src.len = E.trio_len; src.base = E.trio_base; }
     BBState s;
     BBStepOut o;
     int action = 0;
     const uint64_t env_id = (uint64_t)(E.env_offset + (live ? i : 0));
     if (live) {
         bb_load_state(E, i, s);
-        if (RANDOM) bb_action_mask(s, &T, o.mask);
-        else action = actions[i];
+        if (RANDOM) {
+            if (mask_in) {
+                // the caller hands back the mask the previous step / reset wrote for this state
+                const int64_t ms = E.out_stride ? E.out_stride : E.n;
+                o.mask[0] = mask_in[i]; o.mask[1] = mask_in[ms + i]; o.mask[2] = mask_in[2 * ms + i];
+            } else {
+                bb_action_mask(s, &T, o.mask);
+            }
+        } else {
+            action = actions[i];
+        }
     } else {
         s.board = 0; s.pieces = 0; s.aux = 0; s.draw_ctr = 0; s.policy_ctr = 0;
         s.score = s.streak = s.moves = s.lines_total = s.max_streak = s.blocks_total = 0;
@@ -260,11 +274,14 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
             mv = bb_env_pre(s, action, &T, o);
         }
         // all 32 lanes take part in the deal, with or without work of their own
-        const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, E.seed, env_id,
+        const uint32_t draws = bb_warp_deal(live && mv.ok && mv.needs_deal, s.board, &T, src, env_id,
                                             s.pieces, s.draw_ctr, pf);
         if (live && mv.ok) {
-            bb_env_post(s, mv, draws, &T, cfg, E.seed, env_id, E.flags, o, E.ep_end ? E.ep_end + i : nullptr);
-            if (RANDOM && o.terminated) { st_eps += 1; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len; }
+            bb_env_post(s, mv, draws, &T, cfg, src, env_id, E.flags, o, E.ep_end ? E.ep_end + i : nullptr);
+            if (o.terminated) {
+                st_eps += 1u; st_score += (unsigned)o.ep_score; st_len += (unsigned)o.ep_len;
+                st_max = max(st_max, (unsigned)o.ep_score);
+            }
         }
         if (RANDOM && per_step && live) {
             // rollout mode: every step's outputs go to row `step` of [n_steps][...] arrays
@@ -303,15 +320,16 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
         if (board_out) board_out[i] = s.board;          // the next observation (packed)
         if (pieces_out) pieces_out[i] = s.pieces;
     }
-    if (RANDOM && stats) {
-        // warp-reduce (redux.sync on the 32-bit halves), one atomic per warp per counter
+    if (stats) {
+        // warp-reduce with redux.sync (16-bit limbs of the score sum so that 32 lanes cannot wrap),
+        // one atomic per warp per counter
         const unsigned FULLM = 0xffffffffu;
-        st_eps = __reduce_add_sync(FULLM, (unsigned)st_eps);
-        // 20-bit limbs so that the 32-lane sums cannot wrap
-        st_score = (unsigned long long)__reduce_add_sync(FULLM, (unsigned)(st_score & 0xFFFFFull)) +
-                   ((unsigned long long)__reduce_add_sync(FULLM, (unsigned)((st_score >> 20) & 0xFFFFFull)) << 20) +
-                   ((unsigned long long)__reduce_add_sync(FULLM, (unsigned)(st_score >> 40)) << 40);
-        st_len = __reduce_add_sync(FULLM, (unsigned)st_len);
+        const unsigned long long w_eps = __reduce_add_sync(FULLM, st_eps);
+        const unsigned long long w_score = (unsigned long long)__reduce_add_sync(FULLM, st_score & 0xFFFFu) +
+                                           ((unsigned long long)__reduce_add_sync(FULLM, st_score >> 16) << 16);
+        const unsigned long long w_len = (unsigned long long)__reduce_add_sync(FULLM, st_len & 0xFFFFu) +
+                                         ((unsigned long long)__reduce_add_sync(FULLM, st_len >> 16) << 16);
+        const unsigned w_max = __reduce_max_sync(FULLM, st_max);
         const unsigned long long nlive = __popc(__ballot_sync(0xffffffffu, live));
         if ((threadIdx.x & 31) == 0) {
             BB_PF(const unsigned long long tot = (unsigned long long)(clock64() - pf.t0);
@@ -330,10 +348,13 @@ bb_step_kernel(BBEnvArrays E, BBRewardCfg cfg, const int32_t* __restrict__ actio
                   atomicAdd(&stats[16 + (tot >> 13 > 31 ? 31 : tot >> 13)], 1ull);           // cycles histogram
                   atomicAdd(&stats[48 + (pf.rounds > 7 ? 7 : pf.rounds)], 1ull);)           // rounds histogram
             atomicAdd(&stats[0], nlive * (unsigned long long)n_steps);
-            if (st_eps) {
-                atomicAdd(&stats[1], st_eps);
-                atomicAdd(&stats[2], st_score);
-                atomicAdd(&stats[3], st_len);
+            if (w_eps) {
+                atomicAdd(&stats[1], w_eps);
+                atomicAdd(&stats[2], w_score);
+                atomicAdd(&stats[3], w_len);
+#ifndef BB_PROFILE
+                atomicMax(&stats[4], (unsigned long long)w_max);
+#endif
             }
         }
     }
@@ -350,7 +371,9 @@ bb_reset_kernel(BBEnvArrays E, const uint8_t* __restrict__ reset_mask, uint64_t*
     BBState s;
     bb_load_state(E, i, s);
     if (!reset_mask || reset_mask[i]) {
-        bb_reset_state(s, E.seed, (uint64_t)(E.env_offset + i), E.flags);
+        BBTrioSrc src(E.seed);
+        src.trios = E.trios; src.len = E.trio_len; src.base = E.trio_base;
+        bb_reset_state(s, src, (uint64_t)(E.env_offset + i), E.flags);
         bb_store_state(E, i, s);
     }
     if (mask_out) {
@@ -406,10 +429,17 @@ bb_sample_valid_kernel(BBEnvArrays E, uint64_t call_counter, int32_t* __restrict
 static inline unsigned bb_grid(int64_t n) { return (unsigned)((n + BB_STEP_THREADS - 1) / BB_STEP_THREADS); }
 
 cudaError_t bb_launch_step(const BBEnvArrays& E, const BBRewardCfg& cfg, const int32_t* actions,
-                           float* rewards, uint8_t* terminated, uint64_t* mask_out, int32_t* ep_score,
-                           int32_t* ep_len, uint32_t* info_out, cudaStream_t stream) {
-    bb_step_kernel<false><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, nullptr, nullptr, nullptr);
+                           float* rewards, uint8_t* terminated, uint64_t* mask_out, uint64_t* board_out,
+                           uint32_t* pieces_out, int32_t* ep_score, int32_t* ep_len, uint32_t* info_out,
+                           unsigned long long* stats, cudaStream_t stream) {
+    if (E.trios)
+        bb_step_kernel<false, true><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
+            E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, stats, board_out,
+            pieces_out, nullptr);
+    else
+        bb_step_kernel<false, false><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
+            E, cfg, actions, 1, 0, nullptr, rewards, terminated, mask_out, ep_score, ep_len, info_out, stats, board_out,
+            pieces_out, nullptr);
     return cudaGetLastError();
 }
 
@@ -425,19 +455,41 @@ cudaError_t bb_launch_step_range(const BBEnvArrays& E, const BBRewardCfg& cfg, i
     if (R.ep_end) R.ep_end += off;
     R.out_stride = E.n;
 #define BB_OFF(p) ((p) ? (p) + off : nullptr)
-    bb_step_kernel<false><<<bb_grid(cnt), BB_STEP_THREADS, 0, stream>>>(
-        R, cfg, actions + off, 1, 0, nullptr, BB_OFF(rewards), BB_OFF(terminated), BB_OFF(mask_out), BB_OFF(ep_score),
-        BB_OFF(ep_len), BB_OFF(info_out), nullptr, BB_OFF(board_out), BB_OFF(pieces_out));
+    if (R.trios)
+        bb_step_kernel<false, true><<<bb_grid(cnt), BB_STEP_THREADS, 0, stream>>>(
+            R, cfg, actions + off, 1, 0, nullptr, BB_OFF(rewards), BB_OFF(terminated), BB_OFF(mask_out), BB_OFF(ep_score),
+            BB_OFF(ep_len), BB_OFF(info_out), nullptr, BB_OFF(board_out), BB_OFF(pieces_out), nullptr);
+    else
+        bb_step_kernel<false, false><<<bb_grid(cnt), BB_STEP_THREADS, 0, stream>>>(
+            R, cfg, actions + off, 1, 0, nullptr, BB_OFF(rewards), BB_OFF(terminated), BB_OFF(mask_out), BB_OFF(ep_score),
+            BB_OFF(ep_len), BB_OFF(info_out), nullptr, BB_OFF(board_out), BB_OFF(pieces_out), nullptr);
 #undef BB_OFF
     return cudaGetLastError();
 }
 
 cudaError_t bb_launch_step_random(const BBEnvArrays& E, const BBRewardCfg& cfg, int n_steps, int per_step,
                                   int32_t* actions_out, float* rewards, uint8_t* terminated,
-                                  uint64_t* mask_out, unsigned long long* stats, cudaStream_t stream) {
-    bb_step_kernel<true><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
-        E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats,
-        nullptr, nullptr);
+                                  uint64_t* mask_out, unsigned long long* stats, const uint64_t* mask_in,
+                                  cudaStream_t stream) {
+    if (E.trios)
+        bb_step_kernel<true, true><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
+            E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats,
+            nullptr, nullptr, mask_in);
+    else
+        bb_step_kernel<true, false><<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(
+            E, cfg, nullptr, n_steps, per_step, actions_out, rewards, terminated, mask_out, nullptr, nullptr, nullptr, stats,
+            nullptr, nullptr, mask_in);
+    return cudaGetLastError();
+}
+
+// a new injected trio table restarts every env's candidate stream at draw 0
+__global__ void bb_zero_draw_ctr_kernel(BBEnvArrays E) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E.n) E.s2[i].z = 0u;
+}
+
+cudaError_t bb_launch_zero_draw_ctr(const BBEnvArrays& E, cudaStream_t stream) {
+    bb_zero_draw_ctr_kernel<<<bb_grid(E.n), BB_STEP_THREADS, 0, stream>>>(E);
     return cudaGetLastError();
 }
 

@@ -22,8 +22,9 @@ __constant__ uint64_t c_piece_cells[BB_NUM_PIECES + 3] = BB_PIECE_MASKS;
 // f32 item = (env, channel, row, half) -> 4 values.
 template <bool BF16>
 __device__ __forceinline__ uint64_t bb_obs_plane(const uint64_t* __restrict__ board, const uint32_t* __restrict__ pieces,
-                                                 const uint64_t* cells, int64_t t) {
-    const int64_t env = t >> (BF16 ? 5 : 6);
+                                                 const uint64_t* cells, int64_t t, const int64_t* __restrict__ index = nullptr) {
+    int64_t env = t >> (BF16 ? 5 : 6);
+    if (index) env = __ldg(index + env);          // minibatch gather: output row -> rollout-buffer sample
     const int ch = (int)(t >> (BF16 ? 3 : 4)) & 3;
     if (ch == 0) return __ldg(board + env);
     const uint32_t pw = __ldg(pieces + env);
@@ -32,8 +33,23 @@ __device__ __forceinline__ uint64_t bb_obs_plane(const uint64_t* __restrict__ bo
     return used ? 0ull : cells[id < BB_NUM_PIECES ? id : BB_NUM_PIECES];
 }
 
+// split != NULL (f32 only): the reference's separate arrays — board planes f32[n][8][8] at `obs`, piece
+// planes f32[n][3][8][8] at `split` (engine.get_observation, engine.py:489-507) — instead of one
+// [n][4][8][8] block
 template <bool BF16>
-__device__ __forceinline__ void bb_unpack_obs_item(void* __restrict__ obs, int64_t t, uint64_t plane_bits) {
+__device__ __forceinline__ void bb_unpack_obs_item(void* __restrict__ obs, int64_t t, uint64_t plane_bits,
+                                                   void* __restrict__ split = nullptr) {
+    if (!BF16 && split) {
+        const int64_t env = t >> 6;
+        const int ch = (int)(t >> 4) & 3, q = (int)t & 15;
+        const uint32_t bits = (uint32_t)(plane_bits >> (4 * q)) & 0xFu;
+        float4 v;
+        v.x = (bits & 1u) ? 1.f : 0.f; v.y = (bits & 2u) ? 1.f : 0.f;
+        v.z = (bits & 4u) ? 1.f : 0.f; v.w = (bits & 8u) ? 1.f : 0.f;
+        if (ch == 0) __stcs(reinterpret_cast<float4*>(obs) + env * 16 + q, v);
+        else __stcs(reinterpret_cast<float4*>(split) + env * 48 + (ch - 1) * 16 + q, v);
+        return;
+    }
     if (BF16) {
         const uint32_t bits = (uint32_t)(plane_bits >> (8 * ((int)t & 7))) & 0xFFu;
         uint32_t w[4];                              // bf16 1.0 = 0x3F80
@@ -55,7 +71,7 @@ __device__ __forceinline__ void bb_unpack_obs_item(void* __restrict__ obs, int64
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 bb_unpack_obs_kernel(const uint64_t* __restrict__ board, const uint32_t* __restrict__ pieces,
-                     void* __restrict__ obs, int64_t n) {
+                     void* __restrict__ obs, int64_t n, void* __restrict__ split, const int64_t* __restrict__ index) {
     __shared__ uint64_t cells[BB_NUM_PIECES + 3];
     for (int k = threadIdx.x; k < BB_NUM_PIECES + 3; k += blockDim.x) cells[k] = c_piece_cells[k];
     __syncthreads();
@@ -63,16 +79,16 @@ bb_unpack_obs_kernel(const uint64_t* __restrict__ board, const uint32_t* __restr
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; t + 3 * stride < total; t += 4 * stride) {
-        const uint64_t p0 = bb_obs_plane<BF16>(board, pieces, cells, t);
-        const uint64_t p1 = bb_obs_plane<BF16>(board, pieces, cells, t + stride);
-        const uint64_t p2 = bb_obs_plane<BF16>(board, pieces, cells, t + 2 * stride);
-        const uint64_t p3 = bb_obs_plane<BF16>(board, pieces, cells, t + 3 * stride);
-        bb_unpack_obs_item<BF16>(obs, t, p0);
-        bb_unpack_obs_item<BF16>(obs, t + stride, p1);
-        bb_unpack_obs_item<BF16>(obs, t + 2 * stride, p2);
-        bb_unpack_obs_item<BF16>(obs, t + 3 * stride, p3);
+        const uint64_t p0 = bb_obs_plane<BF16>(board, pieces, cells, t, index);
+        const uint64_t p1 = bb_obs_plane<BF16>(board, pieces, cells, t + stride, index);
+        const uint64_t p2 = bb_obs_plane<BF16>(board, pieces, cells, t + 2 * stride, index);
+        const uint64_t p3 = bb_obs_plane<BF16>(board, pieces, cells, t + 3 * stride, index);
+        bb_unpack_obs_item<BF16>(obs, t, p0, split);
+        bb_unpack_obs_item<BF16>(obs, t + stride, p1, split);
+        bb_unpack_obs_item<BF16>(obs, t + 2 * stride, p2, split);
+        bb_unpack_obs_item<BF16>(obs, t + 3 * stride, p3, split);
     }
-    for (; t < total; t += stride) bb_unpack_obs_item<BF16>(obs, t, bb_obs_plane<BF16>(board, pieces, cells, t));
+    for (; t < total; t += stride) bb_unpack_obs_item<BF16>(obs, t, bb_obs_plane<BF16>(board, pieces, cells, t, index), split);
 }
 
 template <bool F32>
@@ -106,24 +122,66 @@ bb_unpack_mask_kernel(const uint64_t* __restrict__ mask, int64_t stride, void* _
     }
 }
 
+static void bb_launch_obs_planes(const uint64_t* board, const uint32_t* pieces, void* obs, int obs_dtype, int64_t n,
+                                 void* split, const int64_t* index, cudaStream_t stream) {
+    const int64_t threads = n * (obs_dtype == 1 ? 32 : 64);
+    int64_t blocks = (threads + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;        // grid-stride: 8 resident blocks per SM x 2 waves
+    const unsigned grid = (unsigned)blocks;
+    if (obs_dtype == 1) bb_unpack_obs_kernel<true><<<grid, 256, 0, stream>>>(board, pieces, obs, n, nullptr, index);
+    else bb_unpack_obs_kernel<false><<<grid, 256, 0, stream>>>(board, pieces, obs, n, split, index);
+}
+
 cudaError_t bb_launch_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask,
                                  int64_t mask_stride, void* obs_nchw, int obs_dtype, void* mask_dense,
-                                 int mask_dtype, int64_t n, cudaStream_t stream) {
+                                 int mask_dtype, int64_t n, cudaStream_t stream, void* pieces_split) {
     if (n <= 0) return cudaSuccess;
-    if (obs_nchw) {
-        const int64_t threads = n * (obs_dtype == 1 ? 32 : 64);
-        int64_t blocks = (threads + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;        // grid-stride: 8 resident blocks per SM x 2 waves
-        const unsigned grid = (unsigned)blocks;
-        if (obs_dtype == 1) bb_unpack_obs_kernel<true><<<grid, 256, 0, stream>>>(board, pieces, obs_nchw, n);
-        else bb_unpack_obs_kernel<false><<<grid, 256, 0, stream>>>(board, pieces, obs_nchw, n);
-    }
+    if (obs_nchw) bb_launch_obs_planes(board, pieces, obs_nchw, obs_dtype, n, pieces_split, nullptr, stream);
     if (mask_dense) {
         const int64_t threads = n * 12;
         const unsigned grid = (unsigned)((threads + 255) / 256);
         if (mask_dtype == 0) bb_unpack_mask_kernel<true><<<grid, 256, 0, stream>>>(mask, mask_stride, mask_dense, n);
         else bb_unpack_mask_kernel<false><<<grid, 256, 0, stream>>>(mask, mask_stride, mask_dense, n);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ minibatch gather
+// RolloutBuffer.get_samples (src/agents/ppo.py:171-213): the reference gathers seven arrays of
+// 1.8 KB rows with numpy fancy indexing and uploads them.  Here sample index[b] of the packed
+// device-resident buffer (board u64, pieces u32, mask planes [T][3][N], action, log-prob,
+// advantage, return; T*N samples, flat index t*N + e) becomes row b of the minibatch: the obs
+// planes are expanded by the K2 kernel reading through the index, the scalars and the mask planes
+// [3][B] by one thread per row; advantages are normalised on the way, (a - mean) / (std + 1e-8) in
+// float32 like ppo.py:196.
+__global__ void __launch_bounds__(256)
+bb_gather_rows_kernel(const int64_t* __restrict__ index, int64_t B, int64_t N, const uint64_t* __restrict__ mask,
+                      const int32_t* __restrict__ action, const float* __restrict__ logp, const float* __restrict__ adv,
+                      const float* __restrict__ ret, const float* __restrict__ mean_std, uint64_t* __restrict__ mask_out,
+                      int32_t* __restrict__ action_out, float* __restrict__ logp_out, float* __restrict__ adv_out,
+                      float* __restrict__ ret_out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t j = index[b];
+    const int64_t t = j / N, e = j - t * N;
+    const uint64_t* m = mask + t * 3 * N + e;
+    mask_out[b] = m[0]; mask_out[B + b] = m[N]; mask_out[2 * B + b] = m[2 * N];
+    action_out[b] = action[j];
+    logp_out[b] = logp[j];
+    ret_out[b] = ret[j];
+    const float a = adv[j];
+    adv_out[b] = mean_std ? __fdiv_rn(__fsub_rn(a, mean_std[0]), __fadd_rn(mean_std[1], 1e-8f)) : a;
+}
+
+cudaError_t bb_launch_gather_minibatch(const int64_t* index, int64_t B, int64_t N, const uint64_t* board,
+                                       const uint32_t* pieces, const uint64_t* mask, const int32_t* action,
+                                       const float* logp, const float* adv, const float* ret, const float* mean_std,
+                                       void* obs, int obs_dtype, uint64_t* mask_out, int32_t* action_out, float* logp_out,
+                                       float* adv_out, float* ret_out, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    bb_launch_obs_planes(board, pieces, obs, obs_dtype, B, nullptr, index, stream);
+    bb_gather_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(index, B, N, mask, action, logp, adv, ret, mean_std,
+                                                                          mask_out, action_out, logp_out, adv_out, ret_out);
     return cudaGetLastError();
 }
 
@@ -162,7 +220,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(128)
 bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
                         uint64_t seed, uint64_t call_counter, int mode, int32_t* __restrict__ action,
-                        float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n) {
+                        float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n, int64_t row_offset,
+                        const uint64_t* __restrict__ counter_dev) {
     const int lane = threadIdx.x & 31;
     const int l = lane & 7;                       // lane inside the row group
     const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -245,7 +304,11 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         act = any_valid ? bi : 0;
         pa = any_valid ? best : 0.f;
     } else {
-        const BBPhilox4 r = bb_philox((uint32_t)row, (uint32_t)((uint64_t)row >> 32), (uint32_t)call_counter,
+        // keyed by the GLOBAL row id (env shards on several GPUs draw independent noise) and by a call
+        // counter that may live on the device (a CUDA graph replays the launch with a new value)
+        const uint64_t grow = (uint64_t)(row + row_offset);
+        const uint64_t ctr = call_counter + (counter_dev ? *counter_dev : 0ull);
+        const BBPhilox4 r = bb_philox((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)ctr,
                                       BB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
         const float t = u * ps;
@@ -311,13 +374,14 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
 
 cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
                                     int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
-                                    int32_t* action, float* logp, float* entropy, int64_t n, cudaStream_t stream) {
+                                    int32_t* action, float* logp, float* entropy, int64_t n, cudaStream_t stream,
+                                    int64_t row_offset, const uint64_t* counter_dev) {
     if (n <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n * 8 + 127) / 128);
     if (logits_dtype == 1)
-        bb_masked_sample_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n);
+        bb_masked_sample_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n, row_offset, counter_dev);
     else
-        bb_masked_sample_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n);
+        bb_masked_sample_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n, row_offset, counter_dev);
     return cudaGetLastError();
 }
 

@@ -345,6 +345,26 @@ BB_HD uint32_t bb_draw_trio(uint64_t seed, uint64_t env_id, uint32_t draw) {
     return bb_mulhi(r.x, 37u) | (bb_mulhi(r.y, 37u) << 8) | (bb_mulhi(r.z, 37u) << 16);
 }
 
+// Where candidate trios come from.  Product runs: Philox stream (seed, global env id, draw).
+// Replay / parity runs (bb_env_set_trios): an injected table trios[n][len][3] of piece ids — what
+// the reference's engine.rng.choice(37, size=3) (src/game/pieces.py:350-355) returned, draw by
+// draw — so the reference's own numpy-PCG64 games can be replayed on the GPU.  Row = env id - base;
+// draws past the table wrap around.  Implicitly constructible from a seed (= Philox).
+struct BBTrioSrc {
+    uint64_t seed;
+    const uint8_t* trios;
+    int64_t len, base;
+    BB_HD BBTrioSrc(uint64_t s = 0) : seed(s), trios(nullptr), len(0), base(0) {}
+};
+
+BB_HD uint32_t bb_candidate(const BBTrioSrc& src, uint64_t env_id, uint32_t draw) {
+    if (src.trios) {
+        const uint8_t* t = src.trios + (((int64_t)env_id - src.base) * src.len + (int64_t)(draw % (uint32_t)src.len)) * 3;
+        return (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16);
+    }
+    return bb_draw_trio(src.seed, env_id, draw);
+}
+
 // ---------------------------------------------------------------------------------------
 // trio solvability (engine.py:174-238).  The reference enumerates piece orders and anchors
 // depth-first with line clears after every simulated placement and returns a boolean, so any
@@ -635,24 +655,24 @@ BB_HD float bb_reward(const BBRewardCfg& c, int n_blocks, int lines, bool game_o
 
 // draw until a solvable trio appears, at most 100 candidates (engine.py:155-172) — the
 // sequential form; the step kernel runs the same loop warp-cooperatively (bb_warp_deal)
-BB_HD uint32_t bb_deal(uint64_t board, const BBTables* T, uint64_t seed, uint64_t env_id, uint32_t* draw_ctr) {
+BB_HD uint32_t bb_deal(uint64_t board, const BBTables* T, const BBTrioSrc& src, uint64_t env_id, uint32_t* draw_ctr) {
     uint32_t trio = 0;
     for (int attempt = 0; attempt < 100; ++attempt) {
-        trio = bb_draw_trio(seed, env_id, *draw_ctr);
+        trio = bb_candidate(src, env_id, *draw_ctr);
         *draw_ctr += 1;
         if (bb_solvable(board, T, trio)) break;
     }
     return trio;   // byte 3 = 0: nothing used
 }
 
-BB_HD void bb_reset_state(BBState& s, uint64_t seed, uint64_t env_id, uint32_t flags) {
+BB_HD void bb_reset_state(BBState& s, const BBTrioSrc& src, uint64_t env_id, uint32_t flags) {
     if (flags & BB_FLAG_RESEED_ON_RESET) s.draw_ctr = 0;
     s.board = 0;
     s.score = s.streak = s.moves = s.lines_total = s.max_streak = s.blocks_total = 0;
     s.aux = 0;             // prev_holes = 0, prev center filled = 0 (openness 1.0), not over
     // on an empty board every trio is solvable (checked exhaustively in tests), so the
     // first candidate is always accepted: engine.py:155-172 consumes exactly one draw
-    s.pieces = bb_draw_trio(seed, env_id, s.draw_ctr);
+    s.pieces = bb_candidate(src, env_id, s.draw_ctr);
     s.draw_ctr += 1;
 }
 
@@ -739,7 +759,7 @@ BB_HD BBMove bb_env_pre(BBState& s, int action, const BBTables* T, BBStepOut& o)
 // (engine.py:440-441) — the same three valid masks are the next observation's action mask —
 // then the shaped reward, and the vec-env's auto-reset (wrappers.py:96-102).
 BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTables* T, const BBRewardCfg& cfg,
-                       uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o, BBEpisodeEnd* ep_end = nullptr) {
+                       const BBTrioSrc& src, uint64_t env_id, uint32_t flags, BBStepOut& o, BBEpisodeEnd* ep_end = nullptr) {
     bb_action_mask(s, T, o.mask);
     const bool over = (o.mask[0] | o.mask[1] | o.mask[2]) == 0ull;
     const int h = bb_holes(s.board), ctr = bb_center(s.board);
@@ -761,7 +781,7 @@ BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTab
             ep_end->last_move = o.info;
         }
         if (!(flags & BB_FLAG_NO_AUTO_RESET)) {
-            bb_reset_state(s, seed, env_id, flags);
+            bb_reset_state(s, src, env_id, flags);
             // empty board, nothing used: every in-bounds anchor is valid
             o.mask[0] = T->row[s.pieces & 0xFFu].inb;
             o.mask[1] = T->row[(s.pieces >> 8) & 0xFFu].inb;
@@ -772,16 +792,16 @@ BB_HD void bb_env_post(BBState& s, const BBMove& mv, uint32_t draws, const BBTab
 
 // One env step, sequential form (host build; the kernel composes pre / warp deal / post).
 BB_HD void bb_env_apply(BBState& s, int action, const BBTables* T, const BBRewardCfg& cfg,
-                        uint64_t seed, uint64_t env_id, uint32_t flags, BBStepOut& o) {
+                        const BBTrioSrc& src, uint64_t env_id, uint32_t flags, BBStepOut& o) {
     const BBMove mv = bb_env_pre(s, action, T, o);
     if (!mv.ok) return;
     uint32_t draws = 0;
     if (mv.needs_deal) {
         const uint32_t before = s.draw_ctr;
-        s.pieces = bb_deal(s.board, T, seed, env_id, &s.draw_ctr);
+        s.pieces = bb_deal(s.board, T, src, env_id, &s.draw_ctr);
         draws = s.draw_ctr - before;
     }
-    bb_env_post(s, mv, draws, T, cfg, seed, env_id, flags, o);
+    bb_env_post(s, mv, draws, T, cfg, src, env_id, flags, o);
 }
 
 // k-th valid action (piece-major, then bit order = np.where(mask)[0] order,

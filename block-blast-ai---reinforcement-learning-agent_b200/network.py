@@ -214,8 +214,13 @@ class BlockBlastNetwork(nn.Module):
         self.fc_encoder = nn.Sequential(*fc)
         self.policy_head = nn.Sequential(nn.Linear(fin, 256), nn.ReLU(), nn.Linear(256, action_space_size))
         self.value_head = nn.Sequential(nn.Linear(fin, 128), nn.ReLU(), nn.Linear(128, 1))
-        self._sample_calls = 0
+        # categorical sampling noise (K3, Philox SAMPLE stream): keyed by (sample_seed, global row id =
+        # sample_row_offset + row, call counter).  The counter lives on the device so that a captured
+        # CUDA graph advances it on every replay; it is not a registered buffer (the state_dict stays the
+        # reference's) — PPOAgent.save / load carry it.
         self.sample_seed = 0
+        self.sample_row_offset = 0
+        self._sample_counter = None
         for m in self.modules():                      # reference network.py:122-133
             if isinstance(m, (nn.Linear, nn.Conv2d)):
                 nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
@@ -289,6 +294,22 @@ class BlockBlastNetwork(nn.Module):
         return self.forward(board, pieces)[1]
 
     # ---------------------------------------------------------------- masked categorical head
+    def sample_counter(self, device=None):
+        """int64[1] CUDA tensor: number of sampling calls made so far."""
+        if self._sample_counter is None or (device is not None and self._sample_counter.device != torch.device(device)):
+            dev = device if device is not None else next(self.parameters()).device
+            old = 0 if self._sample_counter is None else int(self._sample_counter.item())
+            self._sample_counter = torch.full((1,), old, dtype=torch.int64, device=dev)
+        return self._sample_counter
+
+    @property
+    def sample_calls(self):
+        return 0 if self._sample_counter is None else int(self._sample_counter.item())
+
+    @sample_calls.setter
+    def sample_calls(self, value):
+        self.sample_counter().fill_(int(value))
+
     def head_from_logits(self, raw_logits, mask_planes, action=None, deterministic=False, need_entropy=True):
         """K3 on raw (unmasked) logits and packed mask planes int64 [3,B]; no autograd."""
         n = raw_logits.shape[0]
@@ -300,9 +321,11 @@ class BlockBlastNetwork(nn.Module):
         ent = torch.empty(n, dtype=torch.float32, device=logits.device) if need_entropy else None
         if action is None:
             act = torch.empty(n, dtype=torch.int32, device=logits.device)
-            self._sample_calls += 1
-            capi.masked_sample(logits, mask_planes, mask_planes.stride(0), self.sample_seed, self._sample_calls,
-                               1 if deterministic else 0, act, logp, ent)
+            ctr = self.sample_counter(logits.device)
+            capi.masked_sample(logits, mask_planes, mask_planes.stride(0), self.sample_seed, 1,
+                               1 if deterministic else 0, act, logp, ent, self.sample_row_offset, ctr)
+            if not deterministic:
+                ctr.add_(1)
         else:
             act = action.to(torch.int32).contiguous()
             capi.masked_sample(logits, mask_planes, mask_planes.stride(0), 0, 0, 2, act, logp, ent)

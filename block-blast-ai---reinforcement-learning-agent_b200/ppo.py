@@ -49,7 +49,10 @@ class PPOConfig:
 
 
 class PPOAgent:
-    def __init__(self, config=None, device=None):
+    def __init__(self, config=None, device=None, seed=0, global_env_offset=0):
+        """``seed`` keys the action-sampling noise (with the global env id and a call counter, so
+        that env shards on several GPUs draw independent noise and an N-GPU run samples what the
+        1-GPU run samples); ``global_env_offset`` = global id of this rank's env 0."""
         if device is None:
             if not torch.cuda.is_available():
                 raise capi.BBGpuError("PPOAgent needs a CUDA device (no CPU fallback)")
@@ -63,6 +66,8 @@ class PPOAgent:
             self.network = self.network.to(memory_format=torch.channels_last)
             self.network.set_fused_bn(self.config.fused_bn)
             torch.backends.cudnn.benchmark = True     # fixed shapes: let cuDNN pick the conv algorithms
+        self.network.sample_seed = int(seed)
+        self.network.sample_row_offset = int(global_env_offset)
         dist.broadcast_module(self.network)
         # fused=True: one multi-tensor kernel per step instead of a foreach sequence (same update rule)
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5,
@@ -202,19 +207,38 @@ class PPOAgent:
 
     # ------------------------------------------------------------------ persistence / modes
     def save(self, path):
-        """Same keys as ppo.py:425-431 so the reference's evaluate.py / GUI can load it."""
-        cfgd = {k: v for k, v in self.config.to_dict().items() if k not in ("precision", "fused_head", "fused_bn")}
-        torch.save({"network_state_dict": self.network.state_dict(),
-                    "optimizer_state_dict": self.optimizer.state_dict(), "config": cfgd}, path)
+        """Same keys as ppo.py:425-431 so the reference's PPOAgent.load / evaluate.py / GUI can read
+        it (tensors and plain Python values only: loads with torch.load(weights_only=True), the
+        default of the reference's torch.load call).  The optimizer state is written in the form a
+        plain torch.optim.Adam on any device accepts: CPU scalar ``step`` counters, no
+        fused / foreach / capturable flags of ours.  ``b200_state`` (ignored by the reference)
+        carries the sampling-noise position for --resume."""
+        cfgd = {k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.to_dict().items()
+                if k not in ("precision", "fused_head", "fused_bn")}
+        opt = self.optimizer.state_dict()
+        opt = {"state": {k: {n: (v.detach().cpu().float().reshape(()) if n == "step" and torch.is_tensor(v) else v)
+                             for n, v in st.items()} for k, st in opt["state"].items()},
+               "param_groups": [{**g, "fused": None, "foreach": None, "capturable": False} for g in opt["param_groups"]]}
+        torch.save({"network_state_dict": self.network.state_dict(), "optimizer_state_dict": opt, "config": cfgd,
+                    "b200_state": {"sample_calls": self.network.sample_calls, "sample_seed": self.network.sample_seed}},
+                   path)
 
     def load(self, path):
-        ck = torch.load(path, map_location=self.device, weights_only=False)
+        ck = torch.load(path, map_location=self.device, weights_only=True)
         self.network.load_state_dict(ck["network_state_dict"])
         if "optimizer_state_dict" in ck:
-            self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+            opt = ck["optimizer_state_dict"]
+            mine = self.optimizer.state_dict()["param_groups"]
+            # keep this optimizer's own execution flags (fused / capturable), take the hyper-parameters
+            groups = [{**g, **{k: m[k] for k in ("fused", "foreach", "capturable") if k in m}}
+                      for g, m in zip(opt["param_groups"], mine)]
+            self.optimizer.load_state_dict({"state": opt["state"], "param_groups": groups})
         if "config" in ck:
-            self.config = PPOConfig.from_dict({**ck["config"], "precision": self.config.precision,
+            cfg = {k: (tuple(v) if isinstance(v, list) else v) for k, v in ck["config"].items()}
+            self.config = PPOConfig.from_dict({**cfg, "precision": self.config.precision,
                                                "fused_head": self.config.fused_head, "fused_bn": self.config.fused_bn})
+        if "b200_state" in ck:
+            self.network.sample_calls = ck["b200_state"].get("sample_calls", 0)
         self.bucket.rebind()
 
     def train(self):

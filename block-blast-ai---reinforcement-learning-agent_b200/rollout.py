@@ -152,13 +152,38 @@ class RolloutBuffer:
                 obs[:, 1 + k] = tmp[:, 0]
         return obs, dense
 
+    def gather(self, idx, mean_std, obs_dtype=torch.float32, out=None):
+        """Minibatch ``idx`` (int64 flat sample indices) of the packed buffer in ONE library call
+        (bb_gather_minibatch): obs planes (B,4,8,8), mask planes int64 [3,B], actions int32, old
+        log-probs, advantages normalised with ``mean_std`` (float32 [2] device tensor), returns.
+        ``out``: a dict of preallocated outputs to fill (static buffers of a captured CUDA graph)."""
+        assert self.piece_planes is None, "gather() needs the packed pieces words"
+        b, dev = idx.numel(), self.device
+        if out is None:
+            out = dict(obs=torch.empty((b, 4, 8, 8), dtype=obs_dtype, device=dev),
+                       mask=torch.empty((3, b), dtype=torch.int64, device=dev),
+                       actions=torch.empty(b, dtype=torch.int32, device=dev),
+                       logp=torch.empty(b, dtype=torch.float32, device=dev),
+                       adv=torch.empty(b, dtype=torch.float32, device=dev),
+                       ret=torch.empty(b, dtype=torch.float32, device=dev))
+        capi.gather_minibatch(idx, self.num_envs, self.boards, self.pieces, self.action_masks, self.actions,
+                              self.log_probs, self.advantages, self.returns, mean_std, out["obs"], out["mask"],
+                              out["actions"], out["logp"], out["adv"], out["ret"])
+        return out
+
     def iter_minibatches(self, batch_size, generator=None, packed_mask=False):
         """Fast path: yields (obs_nchw f32 (B,4,8,8), mask f32 (B,192) [or int64 planes [3,B] with
         packed_mask], actions i64, old_log_probs, normalised advantages, returns), all CUDA tensors."""
         total = self.buffer_size * self.num_envs
         mean, std = self.advantage_mean_std()
-        adv = (self.advantages.view(-1) - mean) / (std + 1e-8)
         perm = torch.randperm(total, device=self.device, generator=generator)
+        if packed_mask and self.piece_planes is None:
+            ms = torch.stack([mean, std]).float()
+            for start in range(0, total, batch_size):
+                g = self.gather(perm[start:start + batch_size], ms)
+                yield g["obs"], g["mask"], g["actions"], g["logp"], g["adv"], g["ret"]
+            return
+        adv = (self.advantages.view(-1) - mean) / (std + 1e-8)
         for start in range(0, total, batch_size):
             idx = perm[start:start + batch_size]
             obs, dense = self._expand(idx, packed_mask and self.piece_planes is None)

@@ -9,8 +9,13 @@ reshapes the packed observation into the reference's layout.
 
 Output modes (``output=``):
   "numpy"   reference-compatible: numpy obs dict / rewards / terminated / truncated / infos.
-            One H2D copy (actions) and one packed D2H copy (41 B/env) per step through
-            ``bb_env_step_host``; the dense float planes are expanded lazily on first access.
+            ``obs_format="dense"`` (default): the observation arrives in the reference's own layout
+            (board (N,8,8) f32, pieces (N,3,8,8) f32, action_mask (N,192) int8), expanded on the
+            device and copied in one 1,221 B/env transfer (``bb_env_step_host_dense``) — what a
+            caller that reads the arrays every step (PPOAgent.select_actions) wants.
+            ``obs_format="lazy"``: one packed D2H copy (41 B/env, ``bb_env_step_host``); the dense
+            arrays are expanded on the host only if somebody asks for them (``LazyObs``) — for
+            callers that consume the packed protocol or touch few observations.
   "torch"   same keys and shapes, CUDA tensors, nothing crosses PCIe (K2 expands on device).
   "packed"  CUDA tensors in the packed protocol: obs = {'board': int64[N], 'pieces': int32[N],
             'mask': int64[3,N]} — what the on-device rollout path consumes.
@@ -139,12 +144,21 @@ class LazyInfos:
     (scripts/train.py:196-201); those come from the step's own outputs.  The other fields are
     read from the env state when first asked for (one device->host state copy)."""
 
-    def __init__(self, venv, terminated, invalid, ep_score, ep_len):
+    def __init__(self, venv, terminated, invalid, ep_score, ep_len, fetch=None):
         self._venv, self._term, self._inv = venv, terminated, invalid
         self._eps, self._epl = ep_score, ep_len
+        self._fetch = fetch            # callable -> (info words, ep_score, ep_len): the step left them on the device
         self._state = None
         self._ends = None
         self._step_id = getattr(venv, "_step_id", 0)
+
+    def _tail(self):
+        """info word / ep_score / ep_len arrays of the step, fetched from the device on first use."""
+        if self._fetch is not None:
+            if self._step_id != getattr(self._venv, "_step_id", 0):
+                raise RuntimeError("infos of an older step: the per-step info arrays have been overwritten")
+            self._inv, self._eps, self._epl = self._fetch()
+            self._fetch = None
 
     def _end(self, i):
         """Episode-end record of env i (terminal state), fetched from the device on first use."""
@@ -167,6 +181,7 @@ class LazyInfos:
             return [self[k] for k in range(*i.indices(len(self)))]
         if i < 0:
             i += len(self)
+        self._tail()
         if bool(self._term[i]):
             # the finished episode (the env itself has already been reset): wrappers.py:97-100
             e = self._end(i)
@@ -203,12 +218,14 @@ class VectorizedBlockBlastEnv:
     continues, True = that behaviour)."""
 
     def __init__(self, num_envs, seed=None, reward_config=None, *, output="numpy",
-                 global_env_offset=0, reseed_on_reset=False, reuse_buffers=False):
+                 global_env_offset=0, reseed_on_reset=False, reuse_buffers=False, obs_format="dense"):
         import torch
         assert output in ("numpy", "torch", "packed")
+        assert obs_format in ("dense", "lazy")
         self.num_envs = int(num_envs)
         self.reward_config = reward_config
         self.output = output
+        self.obs_format = obs_format
         self.global_env_offset = int(global_env_offset)
         self.reseed_on_reset = bool(reseed_on_reset)
         # numpy mode: False = every step returns fresh arrays (reference behaviour); True = zero-copy
@@ -232,6 +249,9 @@ class VectorizedBlockBlastEnv:
         self._d_info = torch.zeros(n, dtype=torch.int32, device=dev)
         self._d_ep_end = torch.zeros(n * 32, dtype=torch.uint8, device=dev)      # episode-end log (32 B records)
         self._handle.set_episode_end_buffer(self._d_ep_end)
+        # episode statistics accumulated by the step kernel: env-steps, episodes, sum of final scores,
+        # sum of episode lengths, max final score (what scripts/train.py:196-201 reads from infos)
+        self.episode_stats = torch.zeros(8, dtype=torch.int64, device=dev)
         self._step_id = 0
         if output == "numpy":
             pin = dict(pin_memory=True)
@@ -239,6 +259,7 @@ class VectorizedBlockBlastEnv:
             # two result sets (double buffering), each ONE pinned block in the library's layout so a
             # step's results arrive in a single transfer
             self._h_sets = [capi.pinned_result_block(n) for _ in range(2)]
+            self._h_dense = [capi.pinned_dense_block(n) for _ in range(2)] if obs_format == "dense" else None
             self._h_flip = 0
         self._dones = np.zeros(n, dtype=bool)
         self._h_actions_np = self._h_actions.numpy() if output == "numpy" else None
@@ -252,10 +273,12 @@ class VectorizedBlockBlastEnv:
     def handle(self):
         return self._handle
 
-    def _obs_device(self):
-        """obs of the current states in the selected device format."""
+    def _obs_device(self, observe=True):
+        """obs of the current states in the selected device format (observe=False: the step kernel
+        has just written board / pieces / mask itself)."""
         torch = self._torch
-        self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
+        if observe:
+            self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
         if self.output == "packed":
             return {"board": self._d_board, "pieces": self._d_pieces, "mask": self._d_mask}
         n = self.num_envs
@@ -264,8 +287,17 @@ class VectorizedBlockBlastEnv:
         capi.unpack_obs(self._d_board, self._d_pieces, self._d_mask, n, obs=obs, mask_dense=dense)
         return {"board": obs[:, 0], "pieces": obs[:, 1:], "action_mask": dense.view(torch.int8), "nchw": obs}
 
+    def _dense_views(self, d):
+        keep = (lambda x: x) if self.reuse_buffers else (lambda x: x.copy())
+        return {"board": keep(d["board"].numpy()), "pieces": keep(d["pieces"].numpy()),
+                "action_mask": keep(d["action_mask"].numpy())}
+
     def _obs_numpy(self):
         t = self._torch
+        if self.obs_format == "dense":
+            d = self._h_dense[self._h_flip]
+            self._handle.observe_host_dense(d["_block"])
+            return self._dense_views(d)
         h = self._h_sets[self._h_flip]
         self._handle.observe(self._d_board, self._d_pieces, self._d_mask)
         h["board"].copy_(self._d_board, non_blocking=True)
@@ -300,23 +332,35 @@ class VectorizedBlockBlastEnv:
                 self._h_actions.numpy()[:] = a      # int cast like int(action) in wrappers.py:94
             self._h_flip ^= 1
             h = self._h_sets[self._h_flip]
-            self._handle.step_host(self._h_actions, h["rewards"], h["term"], h["board"], h["pieces"], h["mask"],
-                                   h["ep_score"], h["ep_len"], h["info"])
             keep = (lambda x: x) if self.reuse_buffers else (lambda x: x.copy())
+
+            def fetch(h=h, keep=keep):
+                # info word / ep_score / ep_len stay on the device until somebody reads infos
+                self._handle.fetch_step_info(h["ep_score"], h["ep_len"], h["info"])
+                return keep(h["info"].numpy().view(np.uint32)), keep(h["ep_score"].numpy()), keep(h["ep_len"].numpy())
+
+            if self.obs_format == "dense":
+                d = self._h_dense[self._h_flip]
+                self._handle.step_host_dense(self._h_actions, d["_block"])
+                rewards = keep(d["rewards"].numpy())
+                term = d["term"].numpy().view(bool) if self.reuse_buffers else d["term"].numpy().astype(bool)
+                return (self._dense_views(d), rewards, term, np.zeros(n, dtype=bool),
+                        LazyInfos(self, term, None, None, None, fetch))
+            self._handle.step_host(self._h_actions, h["rewards"], h["term"], h["board"], h["pieces"], h["mask"],
+                                   None, None, None)
             rewards = keep(h["rewards"].numpy())
             term = h["term"].numpy().view(bool) if self.reuse_buffers else h["term"].numpy().astype(bool)
             obs = LazyObs(keep(h["board"].numpy().view(np.uint64)), keep(h["pieces"].numpy().view(np.uint32)),
                           keep(h["mask"].numpy().view(np.uint64)))
-            infos = LazyInfos(self, term, keep(h["info"].numpy().view(np.uint32)), keep(h["ep_score"].numpy()),
-                              keep(h["ep_len"].numpy()))
-            return obs, rewards, term, np.zeros(n, dtype=bool), infos
+            return obs, rewards, term, np.zeros(n, dtype=bool), LazyInfos(self, term, None, None, None, fetch)
         if isinstance(actions, torch.Tensor):
             self._d_actions.copy_(actions.reshape(-1), non_blocking=True)
         else:
             self._d_actions.copy_(torch.as_tensor(np.asarray(actions).reshape(-1).astype(np.int32)))
+        # the step kernel writes the packed next observation itself (no separate observe launch)
         self._handle.step(self._d_actions, self._d_rewards, self._d_term, self._d_mask, self._d_ep_score,
-                          self._d_ep_len, self._d_info)
-        obs = self._obs_device()
+                          self._d_ep_len, self._d_info, self._d_board, self._d_pieces, self.episode_stats)
+        obs = self._obs_device(observe=False)
         term = self._d_term.bool()
         infos = {"ep_score": self._d_ep_score, "ep_len": self._d_ep_len, "info": self._d_info}
         return obs, self._d_rewards, term, torch.zeros_like(term), infos
@@ -388,15 +432,15 @@ class BlockBlastEnv:
     def _state(self):
         return self._h.get_state()[0]
 
-    def _get_observation(self):
-        s = self._state()
+    def _get_observation(self, s=None):
+        s = self._state() if s is None else s
         self._h.observe(None, None, self._m)
         m = self._m.cpu().numpy().view(np.uint64)
         return {"board": expand_board(np.array([s["board"]]))[0], "pieces": expand_pieces(np.array([s["pieces"]]))[0],
                 "action_mask": expand_mask(m)[0]}
 
-    def _get_info(self, info_word=None):
-        s = self._state()
+    def _get_info(self, info_word=None, s=None):
+        s = self._state() if s is None else s
         info = {"score": int(s["score"]), "moves": int(s["moves"]), "lines_cleared": int(s["lines_total"]),
                 "max_combo": int(s["max_streak"]), "blocks_placed": int(s["blocks_total"]),
                 "board_fill": bin(int(s["board"])).count("1") / 64, "holes": _holes(int(s["board"])),
@@ -414,16 +458,19 @@ class BlockBlastEnv:
         return self._get_observation(), self._get_info()
 
     def step(self, action):
+        torch = self._torch
         self._a.fill_(int(action))
         self._h.step(self._a, self._r, self._t, None, None, None, self._i)
-        word = int(self._i.item()) & 0xFFFFFFFF
-        reward = float(self._r.item())
-        terminated = bool(self._t.item())
+        # one device->host read for the three step outputs, one state copy for obs and info
+        word, rbits, term = torch.stack([self._i[0], self._r.view(torch.int32)[0], self._t[0].to(torch.int32)]).tolist()
+        word &= 0xFFFFFFFF
+        reward = float(np.array([rbits], np.int32).view(np.float32)[0])
+        st = self._state()
         if word & 1:
-            info = self._get_info()
+            info = self._get_info(s=st)
             info["invalid_action"] = True
-            return self._get_observation(), -10.0, False, False, info
-        return self._get_observation(), reward, terminated, False, self._get_info(word)
+            return self._get_observation(st), -10.0, False, False, info
+        return self._get_observation(st), reward, bool(term), False, self._get_info(word, st)
 
     def get_action_mask(self):
         return self._get_observation()["action_mask"].astype(bool)

@@ -15,7 +15,8 @@
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *     calls are asynchronous on it, never synchronise, and never allocate after create
  *     (except the *_host entry points, which copy and synchronise).
- *   - a bb_env lives on the CUDA device current at bb_env_create time; it is not thread-safe.
+ *   - a bb_env lives on the CUDA device current at bb_env_create time; calls made with another
+ *     device current are refused (error code -1); it is not thread-safe.
  *   - bit convention for boards and masks: bit = row*8 + col; action = piece*64 + row*8 + col
  *     (src/environment/block_blast_env.py:104-132).
  *   - action masks are three bit-planes per env stored plane-major: mask[p*n_envs + i].
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 
 /* flags for bb_env_create */
 #define BB_ENV_RESEED_ON_RESET 1u /* every reset restarts the env's trio stream: the reference's
@@ -73,6 +74,18 @@ int64_t bb_env_num_envs(const bb_env* env);
  * NULL switches the log off.  This is the only pointer the library keeps between calls. */
 int bb_env_set_episode_end_buffer(bb_env* env, void* records);
 
+/* Injected candidate trios — the replay / parity mode ("fed the same piece sequences").
+ * h_trios: HOST u8[n_envs][len][3], piece indices in [0,37): entry [i][d] is what the reference's
+ * engine.rng.choice(37, size=3, replace=True) (src/game/pieces.py:350-355, called from
+ * GameEngine._generate_new_pieces, src/game/engine.py:155-172) returns for env i at its d-th call.
+ * The table replaces the env's Philox stream: candidate number d of env i is h_trios[i][d % len],
+ * accepted or rejected by the same solvability rule.  The library keeps its own device copy, sets
+ * every env's draw counter to 0 and synchronises; call bb_env_reset afterwards to start episodes
+ * on the new stream.  With BB_ENV_RESEED_ON_RESET every reset restarts at entry 0, which is the
+ * reference's behaviour for a seeded env (numpy's PCG64 re-seeded on every reset, engine.py:137-138).
+ * h_trios == NULL returns to the Philox streams. */
+int bb_env_set_trios(bb_env* env, const uint8_t* h_trios, int64_t len, void* stream);
+
 /* VectorizedBlockBlastEnv.reset (wrappers.py:53-73).  reset_mask: device u8[n] or NULL (= all).
  * mask_out: device u64[3*n] or NULL. */
 int bb_env_reset(bb_env* env, const uint8_t* reset_mask, uint64_t* mask_out, void* stream);
@@ -86,24 +99,33 @@ int bb_env_reset(bb_env* env, const uint8_t* reset_mask, uint64_t* mask_out, voi
  *   rewards     device f32[n]
  *   terminated  device u8[n]
  *   mask_out    device u64[3*n]   action mask of the state after the step     (may be NULL)
+ *   board_out   device u64[n]     packed next observation: board               (may be NULL)
+ *   pieces_out  device u32[n]     packed next observation: pieces word         (may be NULL)
  *   ep_score    device i32[n]     written only where terminated: info['final_score'] (NULL ok)
  *   ep_len      device i32[n]     written only where terminated: info['moves']       (NULL ok)
  *   info_out    device u32[n]     bit0 invalid_action, bits1-3 lines_cleared, bits4-7
  *                                 blocks_placed, bits8-10 combo_multiplier, bits11-17 candidate
  *                                 trios drawn, bits18-31 score_gained           (NULL ok)
+ *   stats       device u64[5]     accumulated with atomics (NULL ok): env-steps, finished episodes,
+ *                                 sum of their final scores, sum of their lengths, max final score —
+ *                                 the episode statistics scripts/train.py:196-201 collects from infos
  */
 int bb_env_step(bb_env* env, const int32_t* actions, float* rewards, uint8_t* terminated,
-                uint64_t* mask_out, int32_t* ep_score, int32_t* ep_len, uint32_t* info_out,
-                void* stream);
+                uint64_t* mask_out, uint64_t* board_out, uint32_t* pieces_out, int32_t* ep_score,
+                int32_t* ep_len, uint32_t* info_out, uint64_t* stats, void* stream);
 
 /* n_steps of the same step with the uniform-random-valid-action policy of
  * sample_valid_actions (wrappers.py:133-136, block_blast_env.py:318-323) fused in: the action
  * is the k-th set bit of the 192-bit mask, k = mulhi(philox_word, n_valid).  State stays in
  * registers across the n_steps.  Outputs (all may be NULL) describe the LAST step;
- * stats: device u64[4] accumulated with atomics: env-steps, episodes, sum of final scores,
- * sum of episode lengths. */
+ * stats: device u64[5] accumulated with atomics: env-steps, episodes, sum of final scores,
+ * sum of episode lengths, max final score.
+ * mask_in (device u64[3*n] or NULL): the action mask of the CURRENT states exactly as the previous
+ * step / reset call wrote it to its mask_out (it may be the same buffer as mask_out) — the policy
+ * then reads the observation it was given instead of recomputing it from the boards. */
 int bb_env_step_random(bb_env* env, int32_t n_steps, int32_t* actions_out, float* rewards,
-                       uint8_t* terminated, uint64_t* mask_out, uint64_t* stats, void* stream);
+                       uint8_t* terminated, uint64_t* mask_out, uint64_t* stats,
+                       const uint64_t* mask_in, void* stream);
 
 /* Random-policy ROLLOUT: the same n_steps as bb_env_step_random in one launch (state in
  * registers), but every step's outputs are written: actions_out i32[n_steps][n], rewards
@@ -139,13 +161,32 @@ int bb_env_set_state(bb_env* env, const void* host_records, void* stream);
  * the device, steps, copies rewards/terminated/packed obs back, synchronises.  This is the
  * call the numpy-facing VectorizedBlockBlastEnv.step makes.  board/pieces/mask/ep_* may be
  * NULL to skip that copy; h_info receives the per-env info word of bb_env_step.
- * When all eight result arrays are given and sit in ONE host block at the offsets of
- * bb_env_host_layout, they come back in a single 53 B/env transfer instead of eight. */
-int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes);
+ * bb_env_host_layout gives byte offsets {mask, board, rewards, pieces, ep_score, ep_len, info,
+ * terminated} into ONE host block: mask/board/rewards/pieces/terminated form a prefix of
+ * prefix_bytes (41 B/env rounded up to 16), ep_score/ep_len/info follow.  When the host arrays sit
+ * at these offsets the results come back in a single transfer: 41 B/env when the three tail
+ * arrays are NULL, 53 B/env when they are given.  The tail of the LAST host step stays on the
+ * device and can be fetched on demand with bb_env_fetch_step_info (the training loop reads
+ * infos of terminated envs only, scripts/train.py:196-201). */
+int bb_env_host_layout(int64_t n_envs, int64_t offsets8[8], int64_t* total_bytes, int64_t* prefix_bytes);
 int bb_env_step_host(bb_env* env, const int32_t* h_actions, float* h_rewards,
                      uint8_t* h_terminated, uint64_t* h_board, uint32_t* h_pieces,
                      uint64_t* h_mask, int32_t* h_ep_score, int32_t* h_ep_len, uint32_t* h_info,
                      void* stream);
+int bb_env_fetch_step_info(bb_env* env, int32_t* h_ep_score, int32_t* h_ep_len, uint32_t* h_info,
+                           void* stream);
+
+/* The host-buffer step in the REFERENCE'S OWN observation layout, for callers that read the dense
+ * arrays every step (wrappers.py:110-126 returns them; PPOAgent.select_actions reads them):
+ * h_block is one HOST block laid out by bb_env_host_dense_layout, byte offsets {board f32[n][8][8],
+ * pieces f32[n][3][8][8], action_mask i8[n][192], rewards f32[n], terminated u8[n]} = 1,221 B/env.
+ * The observation is expanded on the device (K2) and arrives in ONE transfer; the packed
+ * observation and the info arrays of the step stay in the device staging block
+ * (bb_env_fetch_step_info).  bb_env_observe_host_dense fills the same block for the current
+ * states without stepping (reset; rewards / terminated are left untouched). */
+int bb_env_host_dense_layout(int64_t n_envs, int64_t offsets5[5], int64_t* total_bytes);
+int bb_env_step_host_dense(bb_env* env, const int32_t* h_actions, void* h_block, void* stream);
+int bb_env_observe_host_dense(bb_env* env, void* h_block, void* stream);
 
 /* Observation expansion (engine.get_observation + Piece.to_mask, engine.py:489-507,
  * src/game/pieces.py:39-45; network input cat([board, pieces]), src/models/network.py:152-158).
@@ -157,12 +198,38 @@ int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t*
                   int64_t mask_stride, void* obs_nchw, int obs_dtype, void* mask_dense,
                   int mask_dtype, int64_t n, void* stream);
 
+/* The same expansion into the reference's three separate arrays (wrappers.py:118-126):
+ * board_f32 device f32[n][8][8], pieces_f32 device f32[n][3][8][8], action_mask_i8 device
+ * i8[n][192] (NULL to skip). */
+int bb_unpack_obs_reference_layout(const uint64_t* board, const uint32_t* pieces, const uint64_t* mask,
+                                   int64_t mask_stride, float* board_f32, float* pieces_f32,
+                                   int8_t* action_mask_i8, int64_t n, void* stream);
+
+/* Minibatch assembly of the PPO update (RolloutBuffer.get_samples, src/agents/ppo.py:171-213: the
+ * reference flattens the (T, N) buffer, normalises the advantages and gathers seven arrays by a
+ * random permutation).  Row b of the minibatch is sample index[b] (flat t*n_envs + e) of the
+ * packed device-resident rollout buffer:
+ *   index device i64[batch]; board device u64[T*n_envs]; pieces device u32[T*n_envs];
+ *   mask device u64[T][3][n_envs]; action i32, logp / adv / ret f32 [T*n_envs]
+ *   adv_mean_std device f32[2] or NULL: adv_out = (adv - mean) / (std + 1e-8) (ppo.py:196)
+ *   obs_nchw device [batch,4,8,8] of obs_dtype; mask_out device u64[3][batch];
+ *   action_out i32, logp_out / adv_out / ret_out f32 [batch] */
+int bb_gather_minibatch(const int64_t* index, int64_t batch, int64_t n_envs, const uint64_t* board,
+                        const uint32_t* pieces, const uint64_t* mask, const int32_t* action,
+                        const float* logp, const float* adv, const float* ret,
+                        const float* adv_mean_std, void* obs_nchw, int obs_dtype, uint64_t* mask_out,
+                        int32_t* action_out, float* logp_out, float* adv_out, float* ret_out,
+                        void* stream);
+
 /* Masked categorical head (BlockBlastNetwork.forward masking + get_action_and_value +
  * _masked_entropy, src/models/network.py:172-262) fused in one kernel.
  *   logits  device [n,192] of logits_dtype (BB_F32 / BB_BF16), raw (unmasked)
  *   mask    device u64[3*n] plane-major, plane stride mask_stride
  *   mode 0: sample  action ~ softmax(masked logits) by inverse CDF on a Philox uniform
- *                   (SAMPLE stream: key seed, counter (row, call_counter))
+ *                   (SAMPLE stream: key seed, counter (row_offset + row, call_counter +
+ *                   *call_counter_dev)); row_offset = global id of row 0, so env shards on
+ *                   several GPUs draw independent noise; call_counter_dev (device u64, NULL = 0)
+ *                   lets a captured CUDA graph advance the counter between replays
  *   mode 1: argmax  (deterministic=True)
  *   mode 2: evaluate the actions given in `action` (PPO update path)
  *   action   device i32[n]  (out for modes 0/1, in for mode 2)
@@ -170,7 +237,8 @@ int bb_unpack_obs(const uint64_t* board, const uint32_t* pieces, const uint64_t*
  *   entropy  device f32[n]  masked entropy (network.py:232-262); NULL to skip */
 int bb_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
                      int64_t mask_stride, uint64_t seed, uint64_t call_counter, int mode,
-                     int32_t* action, float* logp, float* entropy, int64_t n, void* stream);
+                     int32_t* action, float* logp, float* entropy, int64_t n, int64_t row_offset,
+                     const uint64_t* call_counter_dev, void* stream);
 
 /* Backward of bb_masked_sample(mode 2) for the PPO update: autograd of log_prob[action] and the
  * masked entropy through softmax / Categorical (network.py:210-262 as differentiated at

@@ -21,12 +21,12 @@ def test_library_exports_every_declared_symbol(libpath):
     hdr = open(os.path.join(ROOT, "include", "bbgpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = sorted(set(re.findall(r"\b(bb_[a-z_0-9]+)\s*\(", hdr)))
-    assert len(names) >= 14, names
+    assert len(names) >= 30, names
     lib = C.CDLL(libpath)
     for n in names:
         assert hasattr(lib, n), "missing symbol " + n
     lib.bb_version.restype = C.c_int
-    assert lib.bb_version() == 1
+    assert lib.bb_version() == 2
 
 
 def test_piece_table_matches_oracle_table(libpath):
@@ -93,12 +93,28 @@ def test_c_abi_error_paths_return_codes_not_crashes(libpath):
     assert lib.bb_env_create(C.byref(h), -5, 0, 0, None, 0) < 0
     assert lib.bb_env_create(C.byref(h), 8, 0, -1, None, 0) < 0 and b"offset" in lib.bb_last_error()
     assert h.value is None
-    lib.bb_env_step.argtypes = [vp] * 9
-    assert lib.bb_env_step(None, None, None, None, None, None, None, None, None) < 0 and b"env is NULL" in lib.bb_last_error()
+    lib.bb_env_step.argtypes = [vp] * 12
+    assert lib.bb_env_step(*([None] * 12)) < 0 and b"env is NULL" in lib.bb_last_error()
     lib.bb_env_reset.argtypes = [vp] * 4
     assert lib.bb_env_reset(None, None, None, None) < 0
-    lib.bb_env_step_random.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
-    assert lib.bb_env_step_random(None, 1, None, None, None, None, None, None) < 0
+    lib.bb_env_step_random.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
+    assert lib.bb_env_step_random(None, 1, None, None, None, None, None, None, None) < 0
+    lib.bb_env_set_trios.argtypes = [vp, vp, i64, vp]
+    assert lib.bb_env_set_trios(None, None, 0, None) < 0 and b"env is NULL" in lib.bb_last_error()
+    lib.bb_env_step_host_dense.argtypes = [vp] * 4
+    assert lib.bb_env_step_host_dense(None, None, None, None) < 0
+    lib.bb_env_fetch_step_info.argtypes = [vp] * 5
+    assert lib.bb_env_fetch_step_info(None, None, None, None, None) < 0
+    off5, off8, tot, pre = (i64 * 5)(), (i64 * 8)(), i64(), i64()
+    lib.bb_env_host_dense_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64)]
+    assert lib.bb_env_host_dense_layout(10, off5, C.byref(tot)) == 0 and tot.value == 12210 and list(off5) == [0, 2560, 10240, 12160, 12200]
+    assert lib.bb_env_host_dense_layout(0, off5, C.byref(tot)) < 0
+    lib.bb_env_host_layout.argtypes = [i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    assert lib.bb_env_host_layout(10, off8, C.byref(tot), C.byref(pre)) == 0
+    assert pre.value == 416 and tot.value == 416 + 120 and list(off8) == [0, 240, 320, 360, 416, 456, 496, 400]
+    lib.bb_gather_minibatch.argtypes = [vp, i64, i64] + [vp] * 9 + [C.c_int] + [vp] * 6
+    assert lib.bb_gather_minibatch(None, 4, 8, *([None] * 9), 0, *([None] * 6)) < 0 and b"NULL" in lib.bb_last_error()
+    assert lib.bb_gather_minibatch(None, 4, 0, *([None] * 9), 0, *([None] * 6)) < 0
     lib.bb_env_destroy.argtypes = [vp]
     assert lib.bb_env_destroy(None) == 0                      # destroying nothing is fine
     lib.bb_env_num_envs.argtypes = [vp]
@@ -107,11 +123,11 @@ def test_c_abi_error_paths_return_codes_not_crashes(libpath):
     lib.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     assert lib.bb_gae(None, None, None, None, 0.99, 0.95, None, None, None, 4, 4, None) < 0 and b"NULL" in lib.bb_last_error()
     assert lib.bb_gae(None, None, None, None, 0.99, 0.95, None, None, None, -1, 4, None) < 0
-    lib.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, vp]
-    assert lib.bb_masked_sample(None, 0, None, 0, 0, 0, 0, None, None, None, 4, None) < 0
+    lib.bb_masked_sample.argtypes = [vp, C.c_int, vp, i64, u64, u64, C.c_int, vp, vp, vp, i64, i64, vp, vp]
+    assert lib.bb_masked_sample(None, 0, None, 0, 0, 0, 0, None, None, None, 4, 0, None, None) < 0
     one = (C.c_char * 64)()
-    assert lib.bb_masked_sample(one, 7, one, 1, 0, 0, 0, one, None, None, 0, None) < 0 and b"dtype" in lib.bb_last_error()
-    assert lib.bb_masked_sample(one, 0, one, 1, 0, 0, 9, one, None, None, 0, None) < 0 and b"mode" in lib.bb_last_error()
+    assert lib.bb_masked_sample(one, 7, one, 1, 0, 0, 0, one, None, None, 0, 0, None, None) < 0 and b"dtype" in lib.bb_last_error()
+    assert lib.bb_masked_sample(one, 0, one, 1, 0, 0, 9, one, None, None, 0, 0, None, None) < 0 and b"mode" in lib.bb_last_error()
     lib.bb_unpack_obs.argtypes = [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, i64, vp]
     assert lib.bb_unpack_obs(None, None, None, 0, one, 0, None, 0, 1, None) < 0          # obs without board/pieces
     assert lib.bb_unpack_obs(one, one, one, 1, one, 5, None, 0, 1, None) < 0 and b"obs_dtype" in lib.bb_last_error()

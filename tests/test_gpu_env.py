@@ -355,3 +355,242 @@ def test_hundred_candidate_exhaustion_on_gpu(torch):
     assert np.array_equal(oo2["board"], go2["board"]) and np.array_equal(oo2["mask"], go2["mask"])
     assert np.array_equal(oo2["rewards"].view(np.uint32), go2["rewards"].view(np.uint32))
     h.close()
+
+
+# ------------------------------------------------------------------ injected candidate trios (bb_env_set_trios)
+def _pcg64_streams(seed, n, L):
+    """What the reference's per-env numpy Generator returns for successive rng.choice(37, size=3)
+    calls (engine.py:109, pieces.py:354), env i seeded with seed + i (wrappers.py:35-38)."""
+    streams = np.zeros((n, L, 3), np.uint8)
+    for i in range(n):
+        rng = np.random.default_rng(seed + i)
+        for d in range(L):
+            streams[i, d] = rng.choice(37, size=3, replace=True)
+    return streams
+
+
+def test_gpu_replays_the_references_own_seeded_pcg64_games(torch):
+    """vec_trace_seeded.npz = VectorizedBlockBlastEnv(4, seed=42) of the unmodified reference: numpy
+    PCG64 trios, re-seeded on every reset.  The GPU plays it from the injected trio table."""
+    from bbgpu import capi
+    tr = np.load(os.path.join(G, "vec_trace_seeded.npz"))
+    n, seed = tr["actions"].shape[1], int(tr["seed"])
+    h = capi.EnvHandle(n, 0, 0, None, capi.ENV_RESEED_ON_RESET)
+    h.set_trios(_pcg64_streams(seed, n, 64))
+    h.reset()
+    B = _dev_buffers(torch, n)
+    h.observe(B["board"], B["pieces"], B["mask"])
+    torch.cuda.synchronize()
+    assert np.array_equal(B["board"].cpu().numpy().view(np.uint64), tr["board0"])
+    assert np.array_equal(_pieces4(B["pieces"].cpu().numpy().view(np.uint32)), tr["pieces0"])
+    assert np.array_equal(B["mask"].cpu().numpy().view(np.uint64).T, tr["mask0"])
+    n_term = 0
+    for t in range(tr["actions"].shape[0]):
+        o = _gpu_step(torch, h, B, tr["actions"][t])
+        assert np.array_equal(o["board"], tr["board"][t]), t
+        assert np.array_equal(_pieces4(o["pieces"]), tr["pieces"][t]), t
+        assert np.array_equal(o["mask"], tr["mask"][t]), t
+        assert np.array_equal(o["rewards"].view(np.uint32), tr["rewards"][t].view(np.uint32)), t
+        assert np.array_equal(o["terminated"].astype(bool), tr["terminated"][t]), t
+        assert np.array_equal((o["info"] & 1).astype(bool), tr["invalid"][t]), t
+        tt = tr["terminated"][t]
+        n_term += int(tt.sum())
+        assert np.array_equal(o["ep_score"][tt], tr["ep_score"][t][tt]), t
+        assert np.array_equal(o["ep_len"][tt], tr["ep_len"][t][tt]), t
+    st = h.get_state()
+    assert np.array_equal(st["score"], tr["score"][-1]) and np.array_equal(st["moves"], tr["moves"][-1])
+    assert np.array_equal(st["lines_total"], tr["lines_total"][-1]) and np.array_equal(st["max_streak"], tr["max_streak"][-1])
+    assert n_term > 20
+    h.close()
+
+
+def test_gpu_replays_reference_play_random_game_kats(torch):
+    """engine_kats.json: GameEngine(seed) first trios and play_random_game(seed) results of the
+    reference (engine.py:538-576) for 40 seeds.  The engine's PCG64 stream feeds both the trio draws
+    and the move choice, so the oracle plays each game once to log (candidate trios, actions); the
+    GPU then plays all 40 games side by side from the injected trios and must end with the
+    REFERENCE's recorded score / moves / lines / max combo / blocks."""
+    from bbgpu import capi
+    from oracle import bb_oracle as O
+    kats = json.load(open(os.path.join(G, "engine_kats.json")))
+    seeds = sorted(int(s) for s in kats["random_game"])
+    logs = []
+    for s in seeds:
+        draw = O.numpy_rng_factory(s)
+        trios = []
+
+        def rec(draw=draw, trios=trios):
+            t = [int(x) for x in draw()]
+            trios.append(t)
+            return t
+        g = O.Game(rec)
+        acts = []
+        while not g.over:
+            mv = [(i, r, c) for i in range(3) if not g.used[i]
+                  for r in range(O.N) for c in range(O.N) if O.fits(g.grid, g.trio[i], r, c)]
+            if not mv:
+                break
+            i, r, c = mv[draw.rng.choice(len(mv))]
+            acts.append(i * 64 + r * 8 + c)
+            g.move(i, r, c)
+        logs.append((trios, acts))
+    n = len(seeds)
+    L = max(len(t) for t, _ in logs) + 1
+    T = max(len(a) for _, a in logs)
+    table = np.zeros((n, L, 3), np.uint8)
+    actions = np.zeros((T + 1, n), np.int32)
+    for k, (trios, acts) in enumerate(logs):
+        table[k, :len(trios)] = trios
+        actions[:len(acts), k] = acts
+    h = capi.EnvHandle(n, 0, 0, None, capi.ENV_NO_AUTO_RESET)
+    h.set_trios(table)
+    h.reset()
+    B = _dev_buffers(torch, n)
+    h.observe(None, B["pieces"], None)
+    torch.cuda.synchronize()
+    first = _pieces4(B["pieces"].cpu().numpy().view(np.uint32))[:, :3]
+    for k, s in enumerate(seeds):
+        if str(s) in kats["first_trio"]:
+            assert first[k].tolist() == kats["first_trio"][str(s)], s
+    done = np.zeros(n, bool)
+    for t in range(T + 1):
+        o = _gpu_step(torch, h, B, actions[t])
+        live = np.array([t < len(a) for _, a in logs])
+        assert not (o["info"][live & ~done] & 1).any(), t          # every logged move is legal on the GPU too
+        assert ((o["info"][~live] & 1) == 1).all()                  # finished games reject everything (-10)
+        done |= o["terminated"].astype(bool)
+    st = h.get_state()
+    for k, s in enumerate(seeds):
+        got = [int(st["score"][k]), int(st["moves"][k]), int(st["lines_total"][k]), int(st["max_streak"][k]),
+               int(st["blocks_total"][k])]
+        assert got == kats["random_game"][str(s)], (s, got)
+        assert int(st["draw_ctr"][k]) == len(logs[k][0])
+    assert done.all()
+    h.close()
+
+
+def test_injected_trios_equal_the_philox_streams_they_copy(torch):
+    """An injected table filled with the env's own Philox candidates reproduces the Philox run
+    (accept / reject decisions, draw counters, wrap-around of a short table is never reached)."""
+    from bbgpu import capi, philox
+    n, seed, off, T = 3000, 9, 500, 150
+    a = capi.EnvHandle(n, seed, off)
+    b = capi.EnvHandle(n, 12345, off)
+    b.set_trios(philox.candidate_trios(seed, off + np.arange(n), 256))
+    b.reset()
+    a.reset()
+    # reset() on `a` consumed one more Philox candidate than the constructor's deal: align b
+    sa = a.get_state()
+    sb = b.get_state()
+    sb["draw_ctr"] = sa["draw_ctr"]
+    sb["pieces"] = sa["pieces"]
+    b.set_state(sb)
+    Ba, Bb = _dev_buffers(torch, n), _dev_buffers(torch, n)
+    rs = np.random.RandomState(1)
+    a.observe(None, None, Ba["mask"])
+    torch.cuda.synchronize()
+    m = Ba["mask"].cpu().numpy().view(np.uint64).T.copy()
+    for t in range(T):
+        bits = np.unpackbits(m.view(np.uint8).reshape(n, 24), axis=1, bitorder="little")
+        acts = (rs.rand(n, 192) * bits).argmax(axis=1).astype(np.int32)
+        ga, gb = _gpu_step(torch, a, Ba, acts), _gpu_step(torch, b, Bb, acts)
+        for k in ("board", "pieces", "mask", "terminated", "info", "ep_score", "ep_len"):
+            assert np.array_equal(ga[k], gb[k]), (t, k)
+        assert np.array_equal(ga["rewards"].view(np.uint32), gb["rewards"].view(np.uint32)), t
+        m = ga["mask"]
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+    b.set_trios(None)                     # back to Philox: the handle keeps working
+    b.step_random(3)
+    torch.cuda.synchronize()
+    a.close(); b.close()
+
+
+def test_step_outputs_board_pieces_stats_and_mask_in(torch):
+    """ABI v2 additions: bb_env_step writes the packed next observation and episode statistics
+    itself; bb_env_step_random fed with the previous mask (mask_in) equals the recomputing form."""
+    from bbgpu import capi
+    n, seed, T = 5000, 21, 60
+    a, b = capi.EnvHandle(n, seed), capi.EnvHandle(n, seed)
+    Ba, Bb = _dev_buffers(torch, n), _dev_buffers(torch, n)
+    sa = torch.zeros(8, dtype=torch.int64, device="cuda")
+    sb = torch.zeros(8, dtype=torch.int64, device="cuda")
+    a.observe(None, None, Ba["mask"])
+    for t in range(T):
+        a.step_random(1, Ba["actions"], Ba["rewards"], Ba["term"], Ba["mask"], sa, mask_in=Ba["mask"])
+        b.step_random(1, Bb["actions"], Bb["rewards"], Bb["term"], Bb["mask"], sb)
+        torch.cuda.synchronize()
+        for k in ("actions", "rewards", "term", "mask"):
+            assert torch.equal(Ba[k], Bb[k]), (t, k)
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+    assert sa.tolist() == sb.tolist() and sa[1].item() > 100 and sa[4].item() >= sa[2].item() / sa[1].item()
+    # the same actions through bb_env_step: board / pieces / stats written by the step kernel
+    c, d = capi.EnvHandle(n, seed), capi.EnvHandle(n, seed)
+    sc = torch.zeros(8, dtype=torch.int64, device="cuda")
+    Bc = _dev_buffers(torch, n)
+    eps = score = length = 0
+    best = 0
+    for t in range(T):
+        d.step_random(1, Bb["actions"], Bb["rewards"], Bb["term"], Bb["mask"], None)
+        c.step(Bb["actions"], Bc["rewards"], Bc["term"], Bc["mask"], Bc["ep_score"], Bc["ep_len"], Bc["info"],
+               board_out=Bc["board"], pieces_out=Bc["pieces"], stats=sc)
+        torch.cuda.synchronize()
+        st = c.get_state()
+        assert np.array_equal(Bc["board"].cpu().numpy().view(np.uint64), st["board"]), t
+        assert np.array_equal(Bc["pieces"].cpu().numpy().view(np.uint32), st["pieces"]), t
+        assert torch.equal(Bc["mask"], Bb["mask"]) and torch.equal(Bc["rewards"], Bb["rewards"])
+        tt = Bc["term"].cpu().numpy().astype(bool)
+        es = Bc["ep_score"].cpu().numpy()[tt]
+        eps += int(tt.sum()); score += int(es.sum()); length += int(Bc["ep_len"].cpu().numpy()[tt].sum())
+        best = max(best, int(es.max()) if len(es) else 0)
+    assert sc.tolist()[:5] == [n * T, eps, score, length, best]
+    assert sc.tolist()[:5] == sa.tolist()[:5]
+    for h in (a, b, c, d):
+        h.close()
+
+
+def test_dense_host_step_equals_packed_host_step(torch):
+    """bb_env_step_host_dense (reference-layout obs in one pinned block) against the packed host
+    step expanded on the host, plus the on-demand info tail (bb_env_fetch_step_info)."""
+    from bbgpu import capi
+    from bbgpu.vec_env import expand_board, expand_pieces, expand_mask
+    n, seed, T = 777, 4, 40
+    a, b = capi.EnvHandle(n, seed), capi.EnvHandle(n, seed)
+    a.step_random(11); b.step_random(11)
+    blk = capi.pinned_result_block(n)
+    dense = capi.pinned_dense_block(n)
+    ha = torch.zeros(n, dtype=torch.int32).pin_memory()
+    tail = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(3)]
+    b.observe_host_dense(dense["_block"])
+    st = b.get_state()
+    assert np.array_equal(dense["board"].numpy(), expand_board(st["board"]))
+    assert np.array_equal(dense["pieces"].numpy(), expand_pieces(st["pieces"]))
+    for t in range(T):
+        a.sample_valid_actions(t + 1, None, ha)
+        if t % 7 == 3:
+            ha.numpy()[::5] = 191                                   # some invalid actions too
+        a.step_host(ha, blk["rewards"], blk["term"], blk["board"], blk["pieces"], blk["mask"], blk["ep_score"],
+                    blk["ep_len"], blk["info"])
+        b.step_host_dense(ha, dense["_block"])
+        assert np.array_equal(dense["rewards"].numpy().view(np.uint32), blk["rewards"].numpy().view(np.uint32)), t
+        assert np.array_equal(dense["term"].numpy(), blk["term"].numpy()), t
+        assert np.array_equal(dense["board"].numpy(), expand_board(blk["board"].numpy().view(np.uint64))), t
+        assert np.array_equal(dense["pieces"].numpy(), expand_pieces(blk["pieces"].numpy().view(np.uint32))), t
+        assert np.array_equal(dense["action_mask"].numpy(), expand_mask(blk["mask"].numpy().view(np.uint64))), t
+        b.fetch_step_info(*tail)
+        tt = blk["term"].numpy().astype(bool)
+        assert np.array_equal(tail[2].numpy(), blk["info"].numpy()), t
+        assert np.array_equal(tail[0].numpy()[tt], blk["ep_score"].numpy()[tt]), t
+        assert np.array_equal(tail[1].numpy()[tt], blk["ep_len"].numpy()[tt]), t
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+    # prefix-only transfer (no info tail requested) leaves the same prefix
+    blk2 = capi.pinned_result_block(n)
+    a2 = capi.EnvHandle(n, seed)
+    a2.set_state(a.get_state())
+    a.sample_valid_actions(99, None, ha)
+    a.step_host(ha, blk["rewards"], blk["term"], blk["board"], blk["pieces"], blk["mask"], blk["ep_score"], blk["ep_len"], blk["info"])
+    a2.step_host(ha, blk2["rewards"], blk2["term"], blk2["board"], blk2["pieces"], blk2["mask"], None, None, None)
+    for k in ("rewards", "term", "board", "pieces", "mask"):
+        assert torch.equal(blk[k], blk2[k]), k
+    assert a.get_state().tobytes() == a2.get_state().tobytes()
+    for h in (a, b, a2):
+        h.close()

@@ -192,7 +192,8 @@ def test_short_training_run_and_checkpoint_keys(torch, tmp_path):
     assert 5 < hist[-1]["avg_length"] < 40 and hist[-1]["episodes"] > 50
     assert np.isfinite([h["policy_loss"] for h in hist]).all() and hist[0]["entropy"] > 0.5
     ck = torch.load(str(tmp_path / "ck" / "final.pt"), weights_only=False)
-    assert set(ck.keys()) == {"network_state_dict", "optimizer_state_dict", "config"}      # ppo.py:425-431
+    # the reference's three keys (ppo.py:425-431) + our resume position, which its load() ignores
+    assert set(ck.keys()) == {"network_state_dict", "optimizer_state_dict", "config", "b200_state"}
     assert "conv_encoder.0.weight" in ck["network_state_dict"] and ck["config"]["num_epochs"] == 2
     a = PPOAgent()
     a.load(str(tmp_path / "ck" / "final.pt"))
