@@ -70,8 +70,10 @@ class PPOAgent:
         self.network.sample_row_offset = int(global_env_offset)
         dist.broadcast_module(self.network)
         # fused=True: one multi-tensor kernel per step instead of a foreach sequence (same update rule)
+        # capturable: the step counters live on the device, so the step can sit inside a CUDA graph
         self.optimizer = torch.optim.Adam(self.network.parameters(), lr=self.config.learning_rate, eps=1e-5,
-                                          fused=self.device.type == "cuda")
+                                          fused=self.device.type == "cuda", capturable=self.device.type == "cuda")
+        self._graph = None
         self.scheduler = None
         self.bucket = dist.FlatGradBucket(self.network.parameters())
 
@@ -128,6 +130,25 @@ class PPOAgent:
         act, logp, _ = self.network.head_from_logits(logits, planes, None, deterministic, need_entropy=False)
         return act, logp, value
 
+    @torch.no_grad()
+    def act_into(self, obs, actions, log_probs, values, x_buf=None):
+        """``act`` on a packed observation with caller-owned outputs (rows of a RolloutBuffer):
+        K2 -> CNN -> K3 writing ``actions`` int32[N] / ``log_probs`` f32[N] in place, ``values`` f32[N]
+        copied.  No allocation of result tensors, no host work besides the launches — the body of a
+        captured rollout graph."""
+        n = obs["board"].shape[0]
+        x = x_buf if x_buf is not None else torch.empty((n, 4, 8, 8), dtype=torch.float32, device=self.device)
+        capi.unpack_obs(obs["board"], obs["pieces"], obs["mask"], obs["mask"].stride(0), obs=x, n=n)
+        logits, value = self._trunk(x)
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        net = self.network
+        ctr = net.sample_counter(self.device)
+        capi.masked_sample(logits.contiguous(), obs["mask"], obs["mask"].stride(0), net.sample_seed, 1, 0, actions,
+                           log_probs, None, net.sample_row_offset, ctr)
+        ctr.add_(1)
+        values.copy_(value)
+
     def select_actions(self, observations, deterministic=False):
         """ppo.py:291-319: numpy in, numpy out."""
         act, logp, value = self.act(observations, deterministic)
@@ -155,31 +176,81 @@ class PPOAgent:
         return self.values(observations).cpu().numpy()
 
     # ------------------------------------------------------------------ update
-    def update(self, buffer, last_values):
-        """ppo.py:330-423.  Returns the reference's metric dict."""
+    def _fused_step(self, obs, mask, actions, old_logp, adv, ret, sums):
+        """One optimiser step on a gathered minibatch (fused loss tail); metric terms added to ``sums``."""
+        cfg = self.config
+        if cfg.precision == "bf16":
+            obs = obs.contiguous(memory_format=torch.channels_last)
+        with self._autocast():
+            logits, values = self.network.trunk(obs)
+        loss, means = PPOLossTail.apply(logits, values.float(), mask, actions, old_logp, adv, ret,
+                                        cfg.clip_epsilon, cfg.value_coef, cfg.entropy_coef)
+        self.bucket.zero()
+        loss.backward()
+        self.bucket.all_reduce_mean()                  # C1: one flat NCCL all-reduce
+        self.bucket.clip_grad_norm_(cfg.max_grad_norm)
+        self.optimizer.step()
+        sums += torch.stack([means[0], means[1], means[2], loss.detach().double(), means[3], means[4]])
+
+    def _graph_step(self, buffer):
+        """The minibatch step as a replayable CUDA graph: gather (bb_gather_minibatch) of the static
+        index tensor, CNN forward / backward, loss tail, gradient all-reduce, clip, Adam — ~250
+        launches collapse into one graph launch, which is what bounds the reference's own schedule
+        (2,048-sample minibatches) on a B200.  Captured once per (buffer, batch size)."""
+        key = (id(buffer), self.config.batch_size)
+        if self._graph is not None and self._graph["key"] == key:
+            return self._graph
+        dev, b = self.device, self.config.batch_size
+        st = {"key": key, "idx": torch.zeros(b, dtype=torch.int64, device=dev),
+              "ms": torch.zeros(2, dtype=torch.float32, device=dev),
+              "sums": torch.zeros(6, dtype=torch.float64, device=dev)}
+        st["out"] = buffer.gather(st["idx"], st["ms"])
+
+        def body():
+            g = buffer.gather(st["idx"], st["ms"], out=st["out"])
+            self._fused_step(g["obs"], g["mask"], g["actions"], g["logp"], g["adv"], g["ret"], st["sums"])
+
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        st["graph"] = graph
+        self._graph = st
+        return st
+
+    def update(self, buffer, last_values, use_graph=False):
+        """ppo.py:330-423.  Returns the reference's metric dict.  ``use_graph``: replay the minibatch
+        step as a CUDA graph (fused path, full minibatches; the first update always runs eagerly so
+        that cuDNN autotuning and the optimiser state exist before the capture)."""
         cfg = self.config
         buffer.compute_returns_and_advantages(last_values, cfg.gamma, cfg.gae_lambda)
         sums = torch.zeros(6, dtype=torch.float64, device=self.device)
         n_updates = 0
         self.bucket.rebind()
         fused = cfg.fused_head and buffer.piece_planes is None
+        total = buffer.buffer_size * buffer.num_envs
+        self._updates_done = getattr(self, "_updates_done", 0) + 1
+        if use_graph and fused and total % cfg.batch_size == 0 and self._updates_done > 1:
+            st = self._graph_step(buffer)
+            mean, std = buffer.advantage_mean_std()
+            st["ms"].copy_(torch.stack([mean, std]).float())
+            st["sums"].zero_()
+            for _ in range(cfg.num_epochs):
+                perm = torch.randperm(total, device=self.device)
+                for start in range(0, total, cfg.batch_size):
+                    st["idx"].copy_(perm[start:start + cfg.batch_size])
+                    st["graph"].replay()
+                    n_updates += 1
+            s = (st["sums"] / max(n_updates, 1)).cpu().tolist()
+            return {"policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
+                    "approx_kl": s[4], "clip_fraction": s[5]}
         for _ in range(cfg.num_epochs):
             for obs, mask, actions, old_logp, adv, ret in buffer.iter_minibatches(cfg.batch_size, packed_mask=fused):
-                if cfg.precision == "bf16":
-                    obs = obs.contiguous(memory_format=torch.channels_last)
                 if fused:           # mask = int64 planes [3,B]: trunk in torch, everything after it in one kernel
-                    with self._autocast():
-                        logits, values = self.network.trunk(obs)
-                    loss, means = PPOLossTail.apply(logits, values.float(), mask, actions, old_logp, adv, ret,
-                                                    cfg.clip_epsilon, cfg.value_coef, cfg.entropy_coef)
-                    self.bucket.zero()
-                    loss.backward()
-                    self.bucket.all_reduce_mean()                  # C1: one flat NCCL all-reduce
-                    self.bucket.clip_grad_norm_(cfg.max_grad_norm)
-                    self.optimizer.step()
-                    sums += torch.stack([means[0], means[1], means[2], loss.detach().double(), means[3], means[4]])
+                    self._fused_step(obs, mask, actions, old_logp, adv, ret, sums)
                     n_updates += 1
                     continue
+                if cfg.precision == "bf16":
+                    obs = obs.contiguous(memory_format=torch.channels_last)
                 with self._autocast():
                     _, new_logp, entropy, values = self.network.evaluate_actions(obs, mask, actions)
                 values = values.float()
@@ -206,8 +277,9 @@ class PPOAgent:
                 "approx_kl": s[4], "clip_fraction": s[5]}
 
     # ------------------------------------------------------------------ persistence / modes
-    def save(self, path):
-        """Same keys as ppo.py:425-431 so the reference's PPOAgent.load / evaluate.py / GUI can read
+    def save(self, path, network_state=None):
+        """``network_state``: write this state_dict instead of the network's current one (best.pt snapshots).
+        Same keys as ppo.py:425-431 so the reference's PPOAgent.load / evaluate.py / GUI can read
         it (tensors and plain Python values only: loads with torch.load(weights_only=True), the
         default of the reference's torch.load call).  The optimizer state is written in the form a
         plain torch.optim.Adam on any device accepts: CPU scalar ``step`` counters, no
@@ -219,7 +291,8 @@ class PPOAgent:
         opt = {"state": {k: {n: (v.detach().cpu().float().reshape(()) if n == "step" and torch.is_tensor(v) else v)
                              for n, v in st.items()} for k, st in opt["state"].items()},
                "param_groups": [{**g, "fused": None, "foreach": None, "capturable": False} for g in opt["param_groups"]]}
-        torch.save({"network_state_dict": self.network.state_dict(), "optimizer_state_dict": opt, "config": cfgd,
+        torch.save({"network_state_dict": network_state if network_state is not None else self.network.state_dict(),
+                    "optimizer_state_dict": opt, "config": cfgd,
                     "b200_state": {"sample_calls": self.network.sample_calls, "sample_seed": self.network.sample_seed}},
                    path)
 

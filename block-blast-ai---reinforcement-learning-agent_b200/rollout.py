@@ -43,11 +43,15 @@ class RolloutBuffer:
         self.device = torch.device(device)
         self.buffer_size, self.num_envs = int(buffer_size), int(num_envs)
         T, N, dev = self.buffer_size, self.num_envs, self.device
-        self.boards = torch.zeros((T, N), dtype=torch.int64, device=dev)
+        # T+1 observation rows: row t is the observation the action of step t was chosen on, row T the
+        # one after the last step.  On the device-resident path the step kernel writes row t+1 itself
+        # (obs_row), so collecting a rollout copies nothing.
+        self.boards = torch.zeros((T + 1, N), dtype=torch.int64, device=dev)
         # piece planes are stored as the packed pieces word when available, else as planes
-        self.pieces = torch.zeros((T, N), dtype=torch.int32, device=dev)
+        self.pieces = torch.zeros((T + 1, N), dtype=torch.int32, device=dev)
         self.piece_planes = None                      # int64 [T,3,N], allocated by the dense path only
-        self.action_masks = torch.zeros((T, 3, N), dtype=torch.int64, device=dev)
+        self.action_masks = torch.zeros((T + 1, 3, N), dtype=torch.int64, device=dev)
+        self.terminated = torch.zeros((T, N), dtype=torch.uint8, device=dev)   # raw done flags of the step kernel
         self.actions = torch.zeros((T, N), dtype=torch.int32, device=dev)
         self.log_probs = torch.zeros((T, N), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((T, N), dtype=torch.float32, device=dev)
@@ -100,6 +104,21 @@ class RolloutBuffer:
         self.ptr += 1
         if self.ptr >= self.buffer_size:
             self.full = True
+
+    def obs_row(self, t):
+        """Packed observation row t (0..T) as the dict the env / agent exchange (views, no copies)."""
+        return {"board": self.boards[t], "pieces": self.pieces[t], "mask": self.action_masks[t]}
+
+    def set_first_obs(self, obs):
+        if obs["board"].data_ptr() != self.boards[0].data_ptr():
+            self.boards[0].copy_(obs["board"], non_blocking=True)
+            self.pieces[0].copy_(obs["pieces"], non_blocking=True)
+            self.action_masks[0].copy_(obs["mask"], non_blocking=True)
+
+    def finish_direct(self):
+        """After a rollout written in place (train.collect_rollout): done flags u8 -> f32, buffer full."""
+        self.dones.copy_(self.terminated)
+        self.ptr, self.full = self.buffer_size, True
 
     def reset(self):
         self.ptr, self.full = 0, False

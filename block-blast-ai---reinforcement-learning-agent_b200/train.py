@@ -39,7 +39,8 @@ def set_seed(seed):
 
 def collect_rollout(vec_env, agent, buffer, obs, ep):
     """scripts/train.py:173-203: one rollout of buffer.buffer_size steps, all on the device.
-    ``ep`` accumulates episode statistics as device scalars [count, sum score, max score, sum len]."""
+    ``ep`` accumulates episode statistics as device scalars [count, sum score, max score, sum len].
+    Generic form over the public step() API; the training loop itself uses RolloutRunner."""
     buffer.reset()
     for _ in range(buffer.buffer_size):
         actions, log_probs, values = agent.act(obs)
@@ -53,6 +54,56 @@ def collect_rollout(vec_env, agent, buffer, obs, ep):
         ep[2] = torch.maximum(ep[2], sc.max())
         ep[3] += torch.where(t, infos["ep_len"], torch.zeros_like(infos["ep_len"])).sum()
     return obs
+
+
+class RolloutRunner:
+    """The collect phase of scripts/train.py:173-207 with every result written in place: K2 -> CNN ->
+    K3 put action / log-prob / value straight into row t of the RolloutBuffer, K1 puts reward, done flag
+    and the packed next observation into rows t / t+1, and the episode statistics the reference reads from
+    ``infos`` (train.py:196-201) accumulate inside K1 (``vec_env.episode_stats``).  Nothing is copied and
+    nothing leaves the device.  With ``use_graph`` the whole T-step rollout plus the bootstrap value pass
+    is captured once as ONE CUDA graph and replayed — at the reference's 64 envs per process the step is
+    ~60 launches of a few microseconds each, i.e. launch-bound when issued from Python."""
+
+    def __init__(self, vec_env, agent, buffer, use_graph=True):
+        self.vec_env, self.agent, self.buffer = vec_env, agent, buffer
+        n, dev = buffer.num_envs, buffer.device
+        self.x_buf = torch.empty((n, 4, 8, 8), dtype=torch.float32, device=dev)
+        self.last_values = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.use_graph, self.graph, self.calls = bool(use_graph), None, 0
+
+    def _body(self):
+        buf, T = self.buffer, self.buffer.buffer_size
+        buf.set_first_obs(buf.obs_row(T))                      # continue from the last observation
+        for t in range(T):
+            self.agent.act_into(buf.obs_row(t), buf.actions[t], buf.log_probs[t], buf.values[t], self.x_buf)
+            self.vec_env.step_into(buf.actions[t], buf.rewards[t], buf.terminated[t], buf.obs_row(t + 1))
+        self.last_values.copy_(self.agent.values(buf.obs_row(T)))
+        buf.finish_direct()
+
+    def run(self):
+        """One rollout; returns the bootstrap values of the observation after the last step."""
+        buf = self.buffer
+        if self.calls == 0:
+            self.vec_env.current_obs_into(buf.obs_row(buf.buffer_size))
+        self.calls += 1
+        if self.use_graph and self.calls > 1:                  # first rollout eager: cuDNN autotuning, allocator
+            if self.graph is None:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            self.graph.replay()
+            buf.ptr, buf.full = buf.buffer_size, True
+        else:
+            self._body()
+        return self.last_values
+
+    def episode_stats(self):
+        """(episodes, sum of final scores, max final score, sum of lengths) since the last call."""
+        st = self.vec_env.episode_stats
+        v = st.tolist()
+        st.zero_()
+        return v[1], v[2], v[4], v[3]
 
 
 def train(config, resume_path=None, seed=42, progress_callback=None, max_updates=None):
@@ -69,6 +120,10 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
         os.makedirs(log_dir, exist_ok=True)
 
     num_envs = tr_c.get("num_envs", 64)                       # whole job; sharded over ranks
+    if num_envs % world:
+        # unequal shards would give the ranks different minibatch counts, i.e. different numbers of
+        # gradient all-reduces per epoch (a hang), and unequal weights in the gradient mean
+        raise ValueError("training.num_envs (%d) must be divisible by the number of GPUs (%d)" % (num_envs, world))
     offset, n_local = dist.shard(num_envs)
     vec_env = VectorizedBlockBlastEnv(n_local, seed=seed, reward_config=rew_c or None, output="packed",
                                       global_env_offset=offset, reseed_on_reset=bool(ours.get("reseed_on_reset", False)))
@@ -77,7 +132,8 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
         gae_lambda=ppo_c.get("gae_lambda", 0.95), clip_epsilon=ppo_c.get("clip_epsilon", 0.2),
         entropy_coef=ppo_c.get("entropy_coef", 0.01), value_coef=ppo_c.get("value_coef", 0.5),
         max_grad_norm=ppo_c.get("max_grad_norm", 0.5), num_epochs=ppo_c.get("num_epochs", 10),
-        batch_size=tr_c.get("batch_size", 2048), precision=ours.get("precision", "fp32")), device)
+        batch_size=tr_c.get("batch_size", 2048), precision=ours.get("precision", "fp32")), device,
+        seed=seed, global_env_offset=offset)                  # sampling noise keyed by (seed, GLOBAL env id, call)
     agent.train()                                             # train mode during rollout too (scripts/train.py:122)
     start_step = 0
     if resume_path and os.path.exists(resume_path):
@@ -91,8 +147,14 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
     total_timesteps = tr_c.get("total_timesteps", 50_000_000)
     log_interval, save_interval = log_c.get("log_interval", 100), log_c.get("save_interval", 1000)
 
-    obs, _ = vec_env.reset()
-    global_step, num_updates, best_score = start_step, 0, 0.0
+    vec_env.reset()
+    use_graph = bool(ours.get("cuda_graph", True))
+    runner = RolloutRunner(vec_env, agent, buffer, use_graph)
+    target_score = ours.get("stop_at_avg_score")              # optional early stop (score-vs-wallclock runs)
+    max_wall_s = ours.get("max_wall_s")                       # optional wall-clock budget
+    best_every_s = float(ours.get("best_save_min_interval_s", 10.0))
+    global_step, num_updates, best_score, recent = start_step, 0, 0.0, []
+    best_state, best_saved_at = None, 0.0
     history = []
     # same files / keys / TensorBoard tags as scripts/train.py:136-137, 231-258 (rank 0 only)
     logger = Logger(log_dir, name="ppo_b200") if rank == 0 else None
@@ -100,24 +162,31 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
     t0 = time.time()
     try:
         while global_step < total_timesteps:
-            ep = [torch.zeros((), dtype=torch.int64, device=device) for _ in range(4)]
-            obs = collect_rollout(vec_env, agent, buffer, obs, ep)
+            last_values = runner.run()
             global_step += num_envs * rollout_steps
-            last_values = agent.values(obs)
-            metrics = agent.update(buffer, last_values)
+            metrics = agent.update(buffer, last_values, use_graph=use_graph)
             num_updates += 1
-            cnt, ssum, smax, lsum = dist.all_reduce_scalars([ep[0].item(), ep[1].item(), 0, ep[3].item()], device=device)
-            smax = dist.all_reduce_scalars([ep[2].item()], op="max", device=device)[0]
+            e_cnt, e_sum, e_max, e_len = runner.episode_stats()
+            cnt, ssum, lsum = dist.all_reduce_scalars([e_cnt, e_sum, e_len], device=device)
+            smax = dist.all_reduce_scalars([e_max], op="max", device=device)[0]
             elapsed = time.time() - t0
             avg_score = ssum / cnt if cnt else 0.0
+            recent.append((cnt, ssum))
+            del recent[:-10]
+            avg10 = sum(x[1] for x in recent) / max(sum(x[0] for x in recent), 1)     # episodes of the last 10 updates
             row = {"step": global_step, "fps": (global_step - start_step) / max(elapsed, 1e-9), "avg_score": avg_score,
                    "max_score": smax, "best_score": max(best_score, avg_score), "avg_length": lsum / cnt if cnt else 0.0,
-                   "episodes": cnt, "wall_s": elapsed, **metrics}
+                   "episodes": cnt, "wall_s": elapsed, "avg_score_10_updates": avg10, **metrics}
             history.append(row)
             if rank == 0:
                 if avg_score > best_score:
+                    # snapshot the weights on the device now (cheap), write best.pt at most every few seconds:
+                    # an update takes tens of milliseconds here and early on nearly every one is a new best
                     best_score = avg_score
-                    agent.save(os.path.join(ckpt_dir, "best.pt"))
+                    best_state = {k: v.detach().clone() for k, v in agent.network.state_dict().items()}
+                if best_state is not None and time.time() - best_saved_at > best_every_s:
+                    agent.save(os.path.join(ckpt_dir, "best.pt"), network_state=best_state)
+                    best_state, best_saved_at = None, time.time()
                 if num_updates % log_interval == 0 or num_updates <= 10 or ours.get("log_every_update"):
                     logger.log(row, global_step)
                     if tb_logger is not None:
@@ -134,8 +203,14 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
                 break
             if max_updates and num_updates >= max_updates:
                 break
+            if target_score and len(recent) == 10 and avg10 >= target_score:
+                break
+            if max_wall_s and elapsed >= max_wall_s:
+                break
     finally:
         if rank == 0:
+            if best_state is not None:
+                agent.save(os.path.join(ckpt_dir, "best.pt"), network_state=best_state)
             agent.save(os.path.join(ckpt_dir, "final.pt"))
             if logger.metrics_history:
                 logger.save_summary()

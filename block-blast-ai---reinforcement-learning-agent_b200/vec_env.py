@@ -365,6 +365,19 @@ class VectorizedBlockBlastEnv:
         infos = {"ep_score": self._d_ep_score, "ep_len": self._d_ep_len, "info": self._d_info}
         return obs, self._d_rewards, term, torch.zeros_like(term), infos
 
+    def step_into(self, actions, rewards, terminated, next_obs):
+        """Device-resident step with caller-owned outputs (one kernel launch, nothing else):
+        ``actions`` int32[N], ``rewards`` f32[N], ``terminated`` u8[N] and the packed observation after
+        the step written straight into ``next_obs`` = {'board', 'pieces', 'mask'} — e.g. rows of a
+        RolloutBuffer.  Episode statistics accumulate in ``self.episode_stats``."""
+        self._step_id += 1
+        self._handle.step(actions, rewards, terminated, next_obs["mask"], None, None, None, next_obs["board"],
+                          next_obs["pieces"], self.episode_stats)
+
+    def current_obs_into(self, obs):
+        """Packed observation of the current states written into ``obs`` (device tensors)."""
+        self._handle.observe(obs["board"], obs["pieces"], obs["mask"])
+
     def get_action_masks(self):
         """wrappers.py:128-131: bool [N,192]."""
         torch = self._torch
@@ -553,9 +566,10 @@ class BlockBlastEnvFlat(BlockBlastEnv):
             "action_mask": _Box(0, 1, (ACTION_SPACE_SIZE,), np.int8),
         })
 
-    def _get_observation(self):
-        base = super()._get_observation()
-        p = int(self._state()["pieces"])
+    def _get_observation(self, s=None):
+        s = self._state() if s is None else s
+        base = super()._get_observation(s)
+        p = int(s["pieces"])
         onehot = np.zeros((3, 37), np.float32)
         used = np.zeros(3, np.float32)
         for i in range(3):

@@ -327,3 +327,62 @@ def test_flat_view_and_game_state_restore(torch):
     assert r == -10.0 and not t and info["invalid_action"] and other.get_state().status == "game_over"
     for e in (flat, ref, other):
         e.close()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_rollout_runner_rows_replay_through_the_oracle(torch, use_graph):
+    """train.RolloutRunner writes every rollout result in place (K3 -> buffer.actions / log_probs, K1 ->
+    rewards / terminated / next packed observation row) and, with use_graph, replays the whole rollout as
+    one CUDA graph.  Three consecutive rollouts (eager first, then capture + replay) are replayed through
+    the C oracle fed the same Philox trio streams and the recorded actions: rewards (bit patterns), done
+    flags, boards, pieces and masks of every step must be identical, the episode statistics K1
+    accumulates must equal the oracle's, and log-probs / values must be those of the actions' rows."""
+    from bbgpu import philox
+    from bbgpu.ppo import PPOAgent, PPOConfig
+    from bbgpu.rollout import RolloutBuffer
+    from bbgpu.train import RolloutRunner
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    from oracle import bb_oracle_c as OC
+    n, T, seed = 96, 24, 11
+    torch.manual_seed(0)
+    agent = PPOAgent(PPOConfig(precision="bf16"), seed=seed)
+    agent.train()
+    venv = VectorizedBlockBlastEnv(n, seed=seed, output="packed")      # dealt once at creation, like the oracle envs
+    ora = OC.CVecEnv(philox.candidate_trios(seed, np.arange(n), 2048))
+    buf = RolloutBuffer(T, n)
+    runner = RolloutRunner(venv, agent, buf, use_graph=use_graph)
+    eps = score = length = 0
+    for it in range(3):
+        lv = runner.run()
+        torch.cuda.synchronize()
+        assert buf.full and lv.shape == (n,) and torch.isfinite(lv).all()
+        acts = buf.actions.cpu().numpy()
+        rew, term = buf.rewards.cpu().numpy(), buf.terminated.cpu().numpy()
+        boards = buf.boards.cpu().numpy().view(np.uint64)
+        pieces = buf.pieces.cpu().numpy().view(np.uint8).reshape(T + 1, n, 4)
+        masks = buf.action_masks.cpu().numpy().view(np.uint64)
+        assert np.array_equal(buf.dones.cpu().numpy(), term.astype(np.float32))
+        b0, p0, m0 = ora.export()
+        assert np.array_equal(boards[0], b0) and np.array_equal(pieces[0], p0) and np.array_equal(masks[0].T, m0)
+        for t in range(T):
+            # the sampled action is valid under the mask of the row it was sampled on
+            a = acts[t]
+            assert ((masks[t][a // 64, np.arange(n)] >> (a % 64).astype(np.uint64)) & np.uint64(1)).all(), (it, t)
+            oo = ora.step(a)
+            assert not oo["invalid"].any()
+            assert np.array_equal(oo["rewards"].view(np.uint32), rew[t].view(np.uint32)), (it, t)
+            assert np.array_equal(oo["terminated"], term[t]), (it, t)
+            assert np.array_equal(oo["mask"], masks[t + 1].T), (it, t)
+            assert np.array_equal(oo["board"], boards[t + 1]) and np.array_equal(oo["pieces"], pieces[t + 1]), (it, t)
+            done = oo["terminated"].astype(bool)
+            eps += int(done.sum())
+            score += int(oo["ep_score"][done].sum())
+            length += int(oo["ep_len"][done].sum())
+        assert torch.isfinite(buf.log_probs).all() and (buf.log_probs <= 0).all() and torch.isfinite(buf.values).all()
+    st = venv.episode_stats.cpu().tolist()
+    assert st[0] == 3 * n * T and st[1] == eps and eps > 20 and st[2] == score and st[3] == length
+    # one PPO update from the in-place buffer (graph-replayed minibatch step on the second call)
+    for _ in range(2):
+        m = agent.update(buf, lv, use_graph=use_graph)
+        assert all(np.isfinite(v) for v in m.values()) and m["entropy"] > 0.1
+    venv.close()
