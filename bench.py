@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — env-steps/s of the fused Block Blast step kernel (BASELINE.json config 3:
-random valid-action policy, 262,144 envs per GPU), with roofline, CPU baseline and the
-end-to-end number through the drop-in API.
+random valid-action policy, 262,144 envs per GPU per launch), with roofline, CPU baseline and
+the end-to-end numbers through the drop-in API.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -11,13 +11,19 @@ One "step" = ONE launch of the fused K1 kernel over ONE batch of `--envs` enviro
 solvability search, game over, reward, auto-reset, next mask), reading and writing the full
 packed protocol (129 algorithmic bytes per env-step).  To keep every launch HBM-cold the
 bench rotates over `--batches` independent env batches whose combined footprint exceeds the
-126 MB L2 (stated in config.l2).  Weak scaling: every rank owns its own batches; there is no
-data-path collective (envs are independent), only the timing barrier.
+126 MB L2 (stated in config.l2).  The batches are independent, so consecutive launches
+alternate over `--streams` CUDA streams (default 2): launch k+1 fills the SMs that the few
+long warps of launch k (trio searches) leave idle.  The timed region is a block of exactly K
+launches bracketed by barrier + synchronize; the block is repeated until >= --min-seconds of
+device time have been measured and the MEDIAN block is reported (spread in `timing`).  Weak
+scaling: every rank owns its own batches; there is no data-path collective.
 
-The reference arm (--impl reference) times the CPU restatement of the reference's
-VectorizedBlockBlastEnv(64) + sample_valid_actions loop (oracle/bb_oracle.py, same cell-grid
-algorithm and serial per-env Python loop as the reference; the Python reference itself cannot
-travel to the GPU box) on all host cores (one process per core).
+CPU arm (--impl reference, and the cpu_baseline keys): the REAL reference
+(VectorizedBlockBlastEnv(64, seed=42) + sample_valid_actions loop, scripts/benchmark.py:101-144;
+PPOAgent collect + update, scripts/train.py:169-209) from oracle/_ref (oracle/make_ref.py) when
+it travelled with the snapshot — kind "reference"; the oracle port otherwise — kind "port".
+All CPU legs run on rank 0 BEFORE torch.distributed is initialised, so no GPU spins in an NCCL
+barrier while they run.
 """
 import argparse
 import json
@@ -31,7 +37,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 12.63e6 + 0.05e6   # measured by ncu for one 262,144-env launch (see traffic_source)
+NCU_DRAM_BYTES_PER_LAUNCH = 12.63e6 + 0.05e6   # measured by ncu for one 262,144-env launch (see TRAFFIC_SOURCE)
+TRAFFIC_SOURCE = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                  "(profiles/r1_k1_final_ncu_summary.txt); reads are the 12.6 MB of state, the "
+                  "21 MB of outputs + state write-back were still in the 126 MB L2 when the capture ended")
+BOUND_NOTE = ("integer-issue bound, not HBM bound: ALU pipe 63% busy while an SM is active, 28.9 M warp instructions, "
+              "21.9 of 32 lanes active per instruction (ncu); a lone launch leaves SMs idle while its longest warps drain "
+              "(SMs active 78% of the launch), which the second stream fills")
 ALGO_BYTES_PER_ENV_STEP = 129          # SURVEY.md §8d / DESIGN.md: 48 R + 48 W + 4 + 4 + 1 + 24
 STATE_BYTES, OUT_BYTES = 48, 33
 METRIC = "env_steps_per_sec"
@@ -159,16 +171,17 @@ def cpu_c_port(n_threads, seconds, n_envs=4096):
     return done / (time.perf_counter() - t0), done
 
 
-def cpu_ppo_port(seconds_hint=20.0):
-    """PPO samples/s of the reference's schedule on the host CPU (config 1: 64 envs x 128 steps,
-    10 epochs x 4 minibatches of 2048), from TIMED COMPONENTS: the Python oracle env step, one
-    64-sample CNN forward and one 2048-sample forward+backward+Adam step of the same
-    5.29 M-parameter network in torch on the CPU.  A full iteration takes ~2 minutes on 8 cores
-    (BASELINE.md), so the components are timed and the schedule's total is computed."""
+def cpu_ppo_port(seconds_hint=20.0, threads=None):
+    """Fallback when oracle/_ref is absent: PPO samples/s of the reference's schedule on the host CPU
+    (config 1: 64 envs x 128 steps, 10 epochs x 4 minibatches of 2048), from TIMED COMPONENTS: the Python
+    oracle env step, one 64-sample CNN forward and one 2048-sample forward+backward+Adam step of the same
+    5.29 M-parameter network in torch on the CPU."""
     import numpy as np
     import torch
     from bbgpu.network import BlockBlastNetwork
     from oracle import bb_oracle as O
+    if threads:
+        torch.set_num_threads(int(threads))
     torch.manual_seed(0)
     net = BlockBlastNetwork()
     net.train()
@@ -207,6 +220,42 @@ def cpu_ppo_port(seconds_hint=20.0):
     iteration = 128 * (t_env + t_fwd) + 40 * t_mb
     return 8192 / iteration, dict(env_vec_step_s=t_env, fwd64_s=t_fwd, minibatch2048_step_s=t_mb,
                                   iteration_s=iteration, torch_threads=torch.get_num_threads())
+
+
+def cpu_legs(args):
+    """Every CPU measurement of the default run (rank 0, before any GPU / NCCL work)."""
+    from oracle import ref_runner
+    cores = os.cpu_count() or 1
+    out = {}
+    secs = args.cpu_seconds
+    if ref_runner.available():
+        v1, tot1 = ref_runner.env_loop_all_cores(1, secs)
+        out["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "reference",
+                               "sample": "%d env-steps in %.0f s: the unmodified reference (oracle/_ref) VectorizedBlockBlastEnv(64, seed=42) + "
+                                         "sample_valid_actions loop, serial Python as shipped (wrappers.py:93-108)" % (tot1, secs)}
+        va, tota = ref_runner.env_loop_all_cores(cores, min(secs, 6.0))
+        out["cpu_baseline_all_cores"] = {"value": va, "unit": UNIT, "cores": cores, "kind": "reference",
+                                         "sample": "%d env-steps: the same loop in %d independent processes (one per host core)" % (tota, cores)}
+    else:
+        v1, tot1 = cpu_python_port(1, secs)
+        out["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": "%d env-steps: oracle/bb_oracle.py VecEnv(64) + sample_valid_actions (oracle/_ref absent: run "
+                                         "oracle/make_ref.py where /root/reference is mounted)" % tot1}
+    v_c, tot_c = cpu_c_port(cores, min(secs, 6.0))
+    out["cpu_baseline_c_port"] = {"value": v_c, "unit": UNIT, "cores": cores, "kind": "port",
+                                  "sample": "%d env-steps: oracle/bb_oracle.c random-valid rollout, 4096 envs, OpenMP over all host cores" % tot_c}
+    if not args.no_ppo:
+        if ref_runner.available():
+            v, parts = ref_runner.ppo_iteration(1, cores)
+            out["ppo_cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": parts["torch_threads"], "kind": "reference",
+                                       "sample": "the unmodified reference PPOAgent (oracle/_ref) on the CPU, schedule of scripts/train.py:169-209: "
+                                                 "full 128-step x 64-env collect timed, 1 of the 10 update epochs (4 x 2048) timed and scaled to 10",
+                                       **parts}
+        else:
+            v, parts = cpu_ppo_port(secs, cores)
+            out["ppo_cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": parts["torch_threads"], "kind": "port",
+                                       "sample": "reference schedule (64 envs x 128 steps, 10 epochs x 4 x 2048) computed from timed components", **parts}
+    return out
 
 
 def kernel_rooflines(dev, peak):
@@ -305,62 +354,86 @@ def kernel_rooflines(dev, peak):
     return out
 
 
-def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, chunk):
-    """Masked-PPO collect + GAE + update on the device-resident path (BASELINE config 4 shape:
-    131,072 envs per GPU); returns samples/s and the phase times.  Two warm-up iterations (cuDNN
-    autotuning of the conv shapes happens in the first, allocator growth in the second)."""
+
+FWD_FLOP_PER_SAMPLE = 113.05e6          # BlockBlastNetwork forward
+
+
+def _mfu(samples_per_sec_per_gpu, epochs):
+    """Model FLOP utilisation of the CNN work per collected sample: 1 forward in the collect + epochs x
+    (forward + backward = 3 forwards) in the update, against the measured sustained bf16 matmul rate."""
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) * 1e12
+        src = "MEASURED_PEAKS.json bf16_tflops_sustained"
+    except Exception:
+        peak, src = 1377.7e12, "fallback 1377.7 TF/s"
+    flop = FWD_FLOP_PER_SAMPLE * (1 + 3 * epochs)
+    return {"flop_per_collected_sample": flop, "achieved_tflops_per_gpu": samples_per_sec_per_gpu * flop / 1e12,
+            "mfu": samples_per_sec_per_gpu * flop / peak, "peak_source": src}
+
+
+def gpu_ppo_leg(rank, world, dev, n_envs, T, minibatch, epochs, precision, use_graph, iters, warm):
+    """Masked-PPO collect + GAE + update on the device-resident path; returns samples/s and the phase
+    times of the median timed iteration.  ``warm`` untimed iterations first (cuDNN autotuning, allocator
+    growth, CUDA-graph capture when ``use_graph``)."""
     import torch
     import torch.distributed as dist
     from bbgpu.ppo import PPOAgent, PPOConfig
     from bbgpu.rollout import RolloutBuffer
-    from bbgpu.train import collect_rollout
+    from bbgpu.train import RolloutRunner
     from bbgpu.vec_env import VectorizedBlockBlastEnv
-    agent = PPOAgent(PPOConfig(batch_size=minibatch, num_epochs=epochs, precision=precision), dev)
+    offset = (64 + rank) * n_envs
+    agent = PPOAgent(PPOConfig(batch_size=minibatch, num_epochs=epochs, precision=precision), dev, seed=42,
+                     global_env_offset=offset)
     agent.train()
-    venv = VectorizedBlockBlastEnv(n_envs, seed=42, output="packed", global_env_offset=(64 + rank) * n_envs)
+    venv = VectorizedBlockBlastEnv(n_envs, seed=42, output="packed", global_env_offset=offset)
     buf = RolloutBuffer(T, n_envs, device=dev)
-    obs, _ = venv.reset()
-    orig_act = agent.act
-    agent.act = lambda o, deterministic=False: orig_act(o, deterministic, chunk)
-    times = {}
-    for it in range(3):
-        ep = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(4)]
+    runner = RolloutRunner(venv, agent, buf, use_graph=use_graph)
+    rows = []
+    for it in range(warm + iters):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        obs = collect_rollout(venv, agent, buf, obs, ep)
-        last = agent.values(obs, chunk)
+        last = runner.run()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        metrics = agent.update(buf, last)
+        metrics = agent.update(buf, last, use_graph=use_graph)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t2 = time.perf_counter()
-        times = dict(collect_s=t1 - t0, update_s=t2 - t1, total_s=t2 - t0)
-    tt = torch.tensor([times["total_s"]], dtype=torch.float64, device=dev)
+        if it >= warm:
+            rows.append((t2 - t0, t1 - t0, t2 - t1))
+    rows.sort()
+    tot, col, upd = rows[len(rows) // 2]
+    tt = torch.tensor([tot], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     venv.close()
-    return dict(samples_per_sec=world * n_envs * T / float(tt.item()), envs_per_gpu=n_envs, rollout_steps=T,
-                minibatch=minibatch, epochs=epochs, precision=precision, act_chunk=chunk, **times,
-                entropy=metrics["entropy"], approx_kl=metrics["approx_kl"],
-                network="BlockBlastNetwork 5,290,113 params: convs/linears cuDNN/cuBLAS via PyTorch; BatchNorm+ReLU(+residual) "
-                        "= bb_bn_relu_* kernels, loss tail = bb_ppo_loss (bf16 path)",
+    sps = world * n_envs * T / float(tt.item())
+    return dict(samples_per_sec=sps, envs_per_gpu=n_envs, rollout_steps=T, minibatch_per_gpu=minibatch, epochs=epochs,
+                precision=precision, cuda_graph=bool(use_graph), iterations_timed=iters, collect_s=col, update_s=upd,
+                total_s=tot, total_s_min=rows[0][0], total_s_max=rows[-1][0], entropy=metrics["entropy"],
+                approx_kl=metrics["approx_kl"], **_mfu(sps / world, epochs),
                 grad_allreduce="1 flat NCCL all-reduce of 21.2 MB per optimiser step" if world > 1 else "n/a (1 GPU)")
 
 
 def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: the reference's own CPU implementation of the path on all host cores."""
     if rank != 0:
         return
+    from oracle import ref_runner
     cores = os.cpu_count() or 1
     n_envs = 64
     per_step_s = 0.06                      # ~64 envs x ~1 ms per Python env-step
     budget = min(150.0, max(5.0, (args.steps + args.warmup) * per_step_s))
-    # warm-up + timed steps folded into a time-bounded run per process
     t0 = time.perf_counter()
-    value, total = cpu_python_port(cores, budget, n_envs=n_envs, min_steps=max(1, min(args.steps, 50)))
+    if ref_runner.available():
+        value, total = ref_runner.env_loop_all_cores(cores, budget, n_envs=n_envs, min_steps=max(1, min(args.steps, 50)))
+        kind, what = "reference", "the unmodified reference (oracle/_ref): VectorizedBlockBlastEnv(64, seed=42+1000k) + sample_valid_actions loop"
+    else:
+        value, total = cpu_python_port(cores, budget, n_envs=n_envs, min_steps=max(1, min(args.steps, 50)))
+        kind, what = "port", "oracle/bb_oracle.py (Python restatement of the reference's cell-grid engine; oracle/_ref absent)"
     wall = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_envs * cores / value,
@@ -369,33 +442,47 @@ def run_reference_arm(args, rank, world):
             "config": {"workload": "random valid-action policy, VectorizedBlockBlastEnv(64) per process, "
                                    "%d processes (one per host core)" % cores,
                        "step": "one 64-env vec step per process (bounded sample of config 3)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d env-steps in %.1f s: oracle/bb_oracle.py (Python restatement of the "
-                                       "reference's cell-grid engine, serial 64-env loop) x %d processes"
-                                       % (total, wall, cores)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d env-steps in %.1f s: %s x %d processes" % (total, wall, what, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def _spread(xs, per):
+    xs = sorted(xs)
+    q = lambda f: xs[min(len(xs) - 1, int(f * len(xs)))]
+    return {"blocks": len(xs), "median": _median(xs) / per, "min": xs[0] / per, "p10": q(0.1) / per, "p90": q(0.9) / per,
+            "max": xs[-1] / per}
 
 
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=262144, help="envs per batch (= per launch) per GPU")
     ap.add_argument("--batches", type=int, default=8, help="independent env batches rotated per GPU (L2-cold launches)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent batches alternate over")
     ap.add_argument("--preroll", type=int, default=64, help="untimed random steps to reach the steady-state mix")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 100)")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="repeat the K-step block until this much device time is measured")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps per e2e block; 0 = min(steps, 100)")
+    ap.add_argument("--e2e-min-seconds", type=float, default=2.0)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
-    ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU for the PPO leg (config 4: 1,048,576 / 8)")
+    ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--ppo-envs", type=int, default=131072, help="envs per GPU for the config-4 PPO leg (1,048,576 / 8)")
     ap.add_argument("--ppo-steps", type=int, default=8)
     ap.add_argument("--ppo-minibatch", type=int, default=32768)
-    ap.add_argument("--ppo-epochs", type=int, default=2)
+    ap.add_argument("--ppo-epochs", type=int, default=10, help="the reference's PPOConfig.num_epochs (ppo.py:34)")
     ap.add_argument("--ppo-precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
 
@@ -414,6 +501,10 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # CPU legs first, on rank 0, before CUDA / NCCL exist in this process: the other ranks wait in the
+    # TCP-store rendezvous of init_process_group (a host-side wait, no GPU busy-spin)
+    cpu = cpu_legs(args) if (rank == 0 and not args.no_cpu) else {}
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -421,13 +512,21 @@ def main():
     from bbgpu.vec_env import VectorizedBlockBlastEnv
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    binding = None
+    if world > 1:
+        # host side of the e2e path: keep each rank's Python thread, copy completions and pinned buffers on the
+        # cores / memory of its GPU's NUMA node
+        from bbgpu.dist import pin_to_gpu_numa
+        binding = pin_to_gpu_numa(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    capi.lib()
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=20))
+    L = capi.lib()
 
-    n, M, K, W = args.envs, args.batches, args.steps, max(3, args.warmup)
+    n, M, K, W, S = args.envs, args.batches, args.steps, max(3, args.warmup), max(1, args.streams)
+    assert M % S == 0, "--batches must be a multiple of --streams (a batch always runs on the same stream)"
     seed = 42
     # independent batches; global env ids are disjoint across batches and ranks
     envs, outs = [], []
@@ -437,56 +536,80 @@ def main():
                          rewards=torch.zeros(n, dtype=torch.float32, device=dev),
                          term=torch.zeros(n, dtype=torch.uint8, device=dev),
                          mask=torch.zeros((3, n), dtype=torch.int64, device=dev)))
-    stats = torch.zeros(4, dtype=torch.int64, device=dev)
-    for e in envs:
-        e.step_random(args.preroll)          # desynchronise episodes (all envs start in lockstep)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    for e, o in zip(envs, outs):
+        e.step_random(args.preroll, None, None, None, o["mask"])          # desynchronise episodes (all envs start in lockstep)
     torch.cuda.synchronize()
 
-    def launch(k):
-        b = k % M
-        o = outs[b]
-        envs[b].step_random(1, o["actions"], o["rewards"], o["term"], o["mask"], stats)
+    main_stream = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(S)]
+    sptr = [s.cuda_stream for s in streams]
+    largs = [(e.h, 1, o["actions"].data_ptr(), o["rewards"].data_ptr(), o["term"].data_ptr(), o["mask"].data_ptr(),
+              stats.data_ptr(), o["mask"].data_ptr()) for e, o in zip(envs, outs)]
+    step_random = L.bb_env_step_random
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(W):
-        launch(k)
-    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event() for _ in range(S)]
+
+    def block(k0, count, ptrs):
+        """`count` launches alternating over the streams in `ptrs`; device time of the whole block in ms."""
+        ns = len(ptrs)
+        barrier()
+        ev0.record(main_stream)
+        for s in streams[:ns]:
+            s.wait_event(ev0)
+        for k in range(k0, k0 + count):
+            rc = step_random(*largs[k % M], ptrs[k % ns])       # the policy reads the mask the previous step wrote (mask_in)
+            if rc:
+                raise capi.BBGpuError(capi.last_error())
+        for s, e in zip(streams[:ns], ends):
+            e.record(s)
+            main_stream.wait_event(e)
+        ev1.record(main_stream)
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    block(0, W, sptr)                                         # warm-up
     stats.zero_()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     t_wall0 = time.perf_counter()
-    ev0.record()
-    for k in range(K):
-        launch(W + k)
-    ev1.record()
-    barrier()
+    times, k0, launched = [], W, 0
+    while len(times) < 5 or (sum(times) < args.min_seconds * 1e3 and len(times) < 2000):
+        times.append(block(k0, K, sptr))
+        k0 += K
+        launched += K
     wall = time.perf_counter() - t_wall0
-    ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     s = stats.cpu().tolist()
-    assert s[0] == n * K, "kernel did not process the expected number of env-steps"
+    assert s[0] == n * launched, "kernel did not process the expected number of env-steps"
+    ms = _median(times)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = world * n * K / (ms_max * 1e-3)
 
+    # the same K-launch blocks serialised on ONE stream (launch k+1 waits for the last warp of launch k)
+    t1s = [block(k0 + i * K, K, sptr[:1]) for i in range(max(5, min(len(times), 100)))]
+    ms_single = _median(t1s)
+
     # L2-warm variant (single batch, state+outputs 21 MB stay in L2): reported beside, not as value
+    o0 = outs[0]
     for k in range(20):
-        envs[0].step_random(1, outs[0]["actions"], outs[0]["rewards"], outs[0]["term"], outs[0]["mask"], stats)
+        envs[0].step_random(1, o0["actions"], o0["rewards"], o0["term"], o0["mask"], stats)
     barrier()
     ev0.record()
-    kw = min(K, 1000)
+    kw = 1000
     for k in range(kw):
-        envs[0].step_random(1, outs[0]["actions"], outs[0]["rewards"], outs[0]["term"], outs[0]["mask"], stats)
+        envs[0].step_random(1, o0["actions"], o0["rewards"], o0["term"], o0["mask"], stats)
     ev1.record()
     barrier()
     ms_warm = ev0.elapsed_time(ev1)
@@ -499,61 +622,73 @@ def main():
     ms_fused = ev0.elapsed_time(ev1)
 
     # rollout kernel: one launch = 16 steps, EVERY step's actions/rewards/terminated/masks written ([16, N] arrays)
-    S = 16
-    RA = torch.zeros((S, n), dtype=torch.int32, device=dev); RR = torch.zeros((S, n), dtype=torch.float32, device=dev)
-    RT = torch.zeros((S, n), dtype=torch.uint8, device=dev); RM = torch.zeros((S, 3, n), dtype=torch.int64, device=dev)
+    R = 16
+    RA = torch.zeros((R, n), dtype=torch.int32, device=dev); RR = torch.zeros((R, n), dtype=torch.float32, device=dev)
+    RT = torch.zeros((R, n), dtype=torch.uint8, device=dev); RM = torch.zeros((R, 3, n), dtype=torch.int64, device=dev)
     for b in range(2):
-        envs[b].rollout_random(S, RA, RR, RT, RM, stats)
+        envs[b].rollout_random(R, RA, RR, RT, RM, stats)
     barrier()
     ev0.record()
     for k in range(32):
-        envs[k % M].rollout_random(S, RA, RR, RT, RM, stats)
+        envs[k % M].rollout_random(R, RA, RR, RT, RM, stats)
     ev1.record()
     barrier()
     ms_roll = ev0.elapsed_time(ev1)
     del RA, RR, RT, RM
+    for e in envs:
+        e.close()
+    del outs, largs
+    torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ e2e through the drop-in API
     Ke = args.e2e_steps or min(K, 100)
-    venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n,
-                                   reuse_buffers=True)
-    venv.reset()
-    for _ in range(3):
-        venv.step(venv.sample_valid_actions())
-    barrier()
-    t0 = time.perf_counter()
-    n_term = 0
-    for _ in range(Ke):
-        a = venv.sample_valid_actions()                    # kernel + D2H 4 B/env (numpy actions, as the reference)
-        obs, rew, term, trunc, infos = venv.step(a)        # H2D 4 B/env, K1, D2H packed obs 41 B/env
-        n_term += int(np.count_nonzero(term))              # the caller reads the result (np.sum over bools is 10x slower)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * Ke / float(te.item())
-    # same loop, but the caller touches the dense reference-layout observation every step
-    # (board (N,8,8) f32, pieces (N,3,8,8) f32, action_mask (N,192) int8 expanded on the host)
-    Kd = min(Ke, 5)
-    t0 = time.perf_counter()
-    for _ in range(Kd):
-        obs, rew, term, trunc, infos = venv.step(venv.sample_valid_actions())
-        _ = obs["board"], obs["pieces"], obs["action_mask"]
-    e2e_dense = n * Kd / (time.perf_counter() - t0)
-    h2d = 4 * n
-    d2h = 4 * n + (4 + 1 + 8 + 4 + 24 + 4 + 4) * n
 
-    ppo = None
-    for e in envs:
-        e.close()
-    del outs
+    def e2e_leg(obs_format, min_seconds, touch):
+        venv = VectorizedBlockBlastEnv(n, seed=seed, output="numpy", global_env_offset=(world * M + rank) * n,
+                                       reuse_buffers=True, obs_format=obs_format)
+        venv.reset()
+        for _ in range(3):
+            venv.step(venv.sample_valid_actions())
+        blocks, n_term = [], 0
+        while len(blocks) < 3 or (sum(blocks) < min_seconds and len(blocks) < 500):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                a = venv.sample_valid_actions()                    # kernel + D2H 4 B/env (numpy actions, as the reference)
+                obs, rew, term, trunc, infos = venv.step(a)        # H2D 4 B/env, K1 (+ K2 for dense), one D2H of the result block
+                n_term += int(np.count_nonzero(term))              # the caller reads the result
+                if touch:
+                    touch(obs)
+            barrier()
+            blocks.append(time.perf_counter() - t0)
+        venv.close()
+        med = torch.tensor([_median(blocks)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(med, op=dist.ReduceOp.MAX)
+        return world * n * Ke / float(med.item()), _spread(blocks, Ke * 1e-3)
+
+    e2e_value, e2e_spread = e2e_leg("lazy", args.e2e_min_seconds, None)
+    # reference-layout observation delivered every step: board (N,8,8) f32, pieces (N,3,8,8) f32, action_mask
+    # (N,192) int8 expanded on the DEVICE (K2) and copied in one 1,221 B/env transfer; the caller looks at them
+    e2e_dense, dense_spread = e2e_leg("dense", min(args.e2e_min_seconds, 1.5),
+                                      lambda obs: (obs["board"][::4096, 0, 0].sum(), obs["pieces"][::4096, 0, 0, 0].sum(),
+                                                   obs["action_mask"][::4096, 0].sum()))
+    h2d = 4 * n
+    d2h = 4 * n + 41 * n
     torch.cuda.empty_cache()
-    kernels = kernel_rooflines(dev, load_peaks()[0]) if rank == 0 else None
+
+    kernels = kernel_rooflines(dev, load_peaks()[0]) if (rank == 0 and not args.no_kernels) else None
     torch.cuda.empty_cache()
+    ppo = ppo_ref = None
     if not args.no_ppo:
+        # (a) BASELINE config 4 shape: 131,072 envs per GPU (1,048,576 over 8), the reference's 10 epochs
         ppo = gpu_ppo_leg(rank, world, dev, args.ppo_envs, args.ppo_steps, args.ppo_minibatch, args.ppo_epochs,
-                          args.ppo_precision, None)
+                          args.ppo_precision, False, 1, 2)
+        torch.cuda.empty_cache()
+        # (b) the reference's OWN schedule per GPU (config/default.yaml as scripts/train.py reads it: 64 envs x
+        #     128 steps, minibatch 2048, 10 epochs), CUDA-graph replayed — like-for-like with ppo_cpu_baseline
+        ppo_ref = gpu_ppo_leg(rank, world, dev, 64, 128, 2048, 10, args.ppo_precision, True, 9, 3)
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -564,28 +699,41 @@ def main():
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": "random valid-action policy, %d envs per GPU per launch (BASELINE config 3)" % n,
-                       "envs_per_gpu_per_launch": n, "batches_rotated": M, "seed": seed,
+                       "envs_per_gpu_per_launch": n, "batches_rotated": M, "streams": S, "seed": seed,
                        "l2": "rotating %d independent env batches per GPU: %.0f MB of state+outputs > 126 MB L2, "
                              "every launch reads its state from HBM" % (M, M * n * (STATE_BYTES + OUT_BYTES) / 1e6),
-                       "protocol": "packed: state 48 B R+W, action 4 B, reward 4 B, terminated 1 B, mask 24 B",
-                       "parallelism": "env shards per GPU, no data-path collective"},
-            "gpu_launches": K,
+                       "protocol": "packed: state 48 B R+W, action 4 B, reward 4 B, terminated 1 B, mask 24 B R+W",
+                       "parallelism": "env shards per GPU, no data-path collective; launches of independent batches "
+                                      "alternate over %d streams" % S},
+            "timing": {"block_steps": K, "what": "device ms per step, one entry per timed block of K launches "
+                       "(barrier + synchronize on both sides); value = median block", **_spread(times, K),
+                       "timed_device_s": sum(times) * 1e-3, "launches_timed": launched},
+            "gpu_launches": launched,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                           "(profiles/r1_k1_final_ncu_summary.txt); reads are the 12.6 MB of state, the "
-                                           "21 MB of outputs + state write-back were still in the 126 MB L2 when the capture ended",
-                         "bound_note": "integer-issue bound, not HBM bound: ALU pipe 63% busy while an SM is active, SMs active 78% "
-                                       "of the launch, 28.9 M warp instructions, 21.9 of 32 lanes active per instruction (ncu)",
-                         "kernel": "bb_step_kernel<true>",
+                         "traffic_source": TRAFFIC_SOURCE,
+                         "bound_note": BOUND_NOTE,
+                         "kernel": "bb_step_kernel<true,false>",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n, "peak_source": peak_src,
-                         "launch_us": per_launch_s * 1e6},
+                         "launch_us": per_launch_s * 1e6,
+                         "launch_us_is": "block time / K with launches of independent batches overlapping on %d streams" % S,
+                         "launch_us_single_stream": ms_single / K * 1e3,
+                         "frac_single_stream": ALGO_BYTES_PER_ENV_STEP * n / (ms_single * 1e-3 / K) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "dense_obs_materialised_env_steps_per_sec_rank0": e2e_dense, "api": "VectorizedBlockBlastEnv(output='numpy', reuse_buffers=True): sample_valid_actions() + "
-                                        "step(actions); numpy results are zero-copy views of double-buffered pinned memory, "
-                                        "packed obs expanded lazily on host"},
+                    "steps_per_block": Ke, "timing_ms_per_step": e2e_spread,
+                    "observation": "PACKED / LAZY: the step returns board u64, pieces u32 and 3 x u64 mask words per env (41 B/env with "
+                                   "reward and done flag); the reference-layout float arrays are only built if the caller indexes obs[...]",
+                    "api": "VectorizedBlockBlastEnv(output='numpy', obs_format='lazy', reuse_buffers=True): sample_valid_actions() + "
+                           "step(actions); numpy results are zero-copy views of double-buffered pinned memory",
+                    "dense": {"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n + 1221 * n,
+                              "timing_ms_per_step": dense_spread,
+                              "observation": "DENSE reference layout delivered every step (wrappers.py:118-126): board (N,8,8) f32, pieces "
+                                             "(N,3,8,8) f32, action_mask (N,192) int8, expanded on the device by K2 and copied in one block",
+                              "api": "VectorizedBlockBlastEnv(output='numpy', obs_format='dense', reuse_buffers=True)"}},
             "clocks": clocks,
-            "extra": {"l2_warm_single_batch_env_steps_per_sec": n * kw / (ms_warm * 1e-3),
+            "host_binding_rank0": binding,
+            "extra": {"single_stream_env_steps_per_sec": n * K / (ms_single * 1e-3),
+                      "l2_warm_single_batch_env_steps_per_sec": n * kw / (ms_warm * 1e-3),
                       "fused_256_step_launch_env_steps_per_sec": n * 256 / (ms_fused * 1e-3),
                       "rollout16_all_outputs_env_steps_per_sec": n * 16 * 32 / (ms_roll * 1e-3),
                       "episodes": s[1], "mean_episode_len": (s[3] / s[1]) if s[1] else None,
@@ -594,21 +742,16 @@ def main():
         line["kernels"] = kernels
         if ppo is not None:
             line["ppo"] = ppo
-        if not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v_py, tot_py = cpu_python_port(1, args.cpu_seconds)
-            v_c, tot_c = cpu_c_port(cores, min(args.cpu_seconds, 10.0))
-            line["cpu_baseline"] = {"value": v_py, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "%d env-steps: oracle/bb_oracle.py VecEnv(64) + sample_valid_actions, "
-                                              "serial Python like the reference (wrappers.py:93-108)" % tot_py}
-            line["cpu_baseline_c_port"] = {"value": v_c, "unit": UNIT, "cores": cores, "kind": "port",
-                                           "sample": "%d env-steps: oracle/bb_oracle.c random-valid rollout, 4096 envs, "
-                                                     "OpenMP over all host cores" % tot_c}
-            if ppo is not None:
-                v_ppo, parts = cpu_ppo_port(args.cpu_seconds)
-                line["ppo"]["cpu_baseline"] = {"value": v_ppo, "unit": "samples/s", "cores": parts["torch_threads"],
-                                               "kind": "port", "sample": "reference schedule (64 envs x 128 steps, 10 epochs x 4 x 2048) "
-                                               "computed from timed components", **parts}
+            line["ppo_reference_schedule"] = ppo_ref
+        for k in ("cpu_baseline", "cpu_baseline_all_cores", "cpu_baseline_c_port"):
+            if k in cpu:
+                line[k] = cpu[k]
+        if ppo is not None and "ppo_cpu_baseline" in cpu:
+            cb = cpu["ppo_cpu_baseline"]
+            line["ppo_reference_schedule"]["cpu_baseline"] = cb
+            line["ppo_reference_schedule"]["ratio_per_gpu_vs_cpu_box"] = ppo_ref["samples_per_sec"] / world / cb["value"]
+            line["ppo"]["cpu_baseline"] = cb
+            line["ppo"]["ratio_per_gpu_vs_cpu_box"] = ppo["samples_per_sec"] / world / cb["value"]
         emit(line)
     if world > 1:
         dist.barrier()

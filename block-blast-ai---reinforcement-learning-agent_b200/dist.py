@@ -110,3 +110,55 @@ def all_reduce_scalars(values, op="sum", device=None):
     if world_size() > 1:
         td.all_reduce(t, op={"sum": td.ReduceOp.SUM, "max": td.ReduceOp.MAX, "min": td.ReduceOp.MIN}[op])
     return t.tolist()
+
+
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa(local_rank, local_world):
+    """Bind this process to host cores next to its GPU: the cores of the GPU's NUMA node (from sysfs via
+    the PCI address), split evenly among the ranks whose GPUs share that node.  Pinned host buffers
+    allocated afterwards are first-touched, hence placed, on that node.  The host-buffer step
+    (bb_env_step_host) is one PCIe transfer + a stream synchronise per step per rank; without the
+    binding eight ranks' Python threads and copy completions migrate over all cores of the box.
+    Returns a dict describing what was done (for the bench line); never raises."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n_gpus = pynvml.nvmlDeviceGetCount()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        order = [int(x) for x in visible.split(",")] if visible and all(x.strip().isdigit() for x in visible.split(",")) else list(range(n_gpus))
+
+        def node_of(idx):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(order[idx])).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:            # nvml prints an 8-digit domain, sysfs a 4-digit one
+                bus = bus[4:]
+            with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+                return int(f.read().strip())
+
+        nodes = [node_of(i) for i in range(local_world)]
+        node = nodes[local_rank]
+        path = "/sys/devices/system/node/node%d/cpulist" % max(node, 0)
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in _parse_cpulist(open(path).read()) if c in allowed] if os.path.exists(path) else allowed
+        if not cpus:
+            cpus = allowed
+        peers = [r for r in range(local_world) if nodes[r] == node]
+        k = peers.index(local_rank)
+        per = max(1, len(cpus) // len(peers))
+        mine = cpus[k * per:(k + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        info = {"numa_node": node, "cpus": "%d-%d (%d cores)" % (mine[0], mine[-1], len(mine)), "gpu_numa_nodes": nodes}
+    except Exception as e:                            # no nvml / sysfs: leave the affinity alone
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
