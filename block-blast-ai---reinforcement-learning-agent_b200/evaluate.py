@@ -18,7 +18,11 @@ from .ppo import PPOAgent
 
 
 @torch.no_grad()
-def evaluate(agent, num_episodes=100, seed=0, deterministic=True, max_steps=10000, reward_config=None):
+def evaluate(agent, num_episodes=100, seed=0, deterministic=True, max_steps=10000, reward_config=None,
+             return_actions=False):
+    """``return_actions``: also return ``actions`` int32 [steps, n] (the action every env was given at every
+    step; entries after an env's game over are ignored by the env) and ``rewards_per_episode`` — enough to
+    replay every episode through another implementation of the rules (tests do, through the oracle)."""
     dev = agent.device
     n = int(num_episodes)
     h = capi.EnvHandle(n, seed, 0, reward_config, capi.ENV_NO_AUTO_RESET)
@@ -32,9 +36,12 @@ def evaluate(agent, num_episodes=100, seed=0, deterministic=True, max_steps=1000
     was_training = agent.training
     agent.eval()                                       # scripts/evaluate.py evaluates in eval mode
     steps = 0
+    log = []
     while steps < max_steps and not bool(done.all()):
         h.observe(board, pieces, mask)
         act, _, _ = agent.act({"board": board, "pieces": pieces, "mask": mask}, deterministic=deterministic)
+        if return_actions:
+            log.append(act.clone())
         h.step(act, rewards, term, None, None, None, None)
         total_reward += torch.where(done, torch.zeros_like(rewards), rewards).double()
         done |= term.bool()
@@ -44,7 +51,12 @@ def evaluate(agent, num_episodes=100, seed=0, deterministic=True, max_steps=1000
     if was_training:
         agent.train()
     scores, lengths = st["score"].astype(np.int64), st["moves"].astype(np.int64)
-    return {"num_episodes": n, "mean_score": float(scores.mean()), "std_score": float(scores.std()),
+    extra = {}
+    if return_actions:
+        extra = {"actions": torch.stack(log).cpu().numpy() if log else np.zeros((0, n), np.int32),
+                 "rewards_per_episode": total_reward.cpu().numpy(), "lines": st["lines_total"].astype(np.int64),
+                 "max_combos": st["max_streak"].astype(np.int64)}
+    return {**extra, "num_episodes": n, "mean_score": float(scores.mean()), "std_score": float(scores.std()),
             "max_score": int(scores.max()), "min_score": int(scores.min()), "mean_length": float(lengths.mean()),
             "max_length": int(lengths.max()), "mean_lines": float(st["lines_total"].mean()),
             "max_combo": int(st["max_streak"].max()), "mean_reward": float(total_reward.mean().item()),

@@ -195,6 +195,7 @@ def record_policy(path):
     import torch
     from models.network import BlockBlastNetwork
     torch.manual_seed(0)
+    np.random.seed(11)        # the reference's sample_valid_actions draws from numpy's GLOBAL generator (block_blast_env.py:323)
     net = BlockBlastNetwork()
     net.eval()
     rs = np.random.RandomState(3)
@@ -229,6 +230,9 @@ def record_policy(path):
 
 def main():
     os.makedirs(HERE, exist_ok=True)
+    if "--only-policy" in sys.argv:
+        record_policy(os.path.join(HERE, "policy_golden.npz"))
+        return
     record_engine_kats(os.path.join(HERE, "engine_kats.json"))
     record_vec_trace(os.path.join(HERE, "vec_trace.npz"), 8, 2500, seed=42)
     record_vec_trace(os.path.join(HERE, "vec_trace_cfg.npz"), 4, 600, seed=7,

@@ -224,6 +224,82 @@ def test_batched_deterministic_evaluation(torch):
     assert agent.training            # mode restored
 
 
+def test_evaluation_episodes_replay_through_the_oracle(torch):
+    """scripts/evaluate.py:23-90 semantics against the oracle: every env plays ONE episode with the argmax
+    policy in eval mode; the logged action sequences are replayed through the Python oracle (reference
+    single-env semantics, no auto-reset) fed the same Philox trio streams — per-episode final score, length,
+    lines cleared, max combo and summed reward must be identical, and every logged action must be the argmax
+    of a valid action (never rejected)."""
+    from bbgpu import philox
+    from bbgpu.evaluate import evaluate
+    from bbgpu.ppo import PPOAgent
+    from oracle import bb_oracle as O
+    torch.manual_seed(5)
+    agent = PPOAgent()
+    n, seed = 48, 9
+    res = evaluate(agent, num_episodes=n, seed=seed, return_actions=True)
+    assert res["finished"] == n and res["actions"].shape[1] == n
+    streams = philox.candidate_trios(seed, np.arange(n), 1024)
+    for i in range(n):
+        it = iter(streams[i])
+        env = O.Env(draw=lambda: next(it))
+        total, t, term, info = 0.0, 0, False, None
+        while not term:
+            _, r, term, _, info = env.step(int(res["actions"][t, i]))
+            assert not info["invalid_action"], (i, t)
+            total += float(np.float32(r))
+            t += 1
+        assert info["score"] == res["scores"][i] and info["moves"] == res["lengths"][i] == t, (i, info, res["scores"][i])
+        assert info["lines_cleared"] == res["lines"][i] and info["max_combo"] == res["max_combos"][i]
+        assert abs(total - res["rewards_per_episode"][i]) < 1e-4 * max(1.0, abs(total))
+    assert res["mean_score"] == float(res["scores"].mean()) and res["max_length"] == int(res["lengths"].max())
+
+
+@pytest.mark.reference_copy
+def test_checkpoint_loads_in_the_references_own_agent(torch, tmp_path):
+    """PPOAgent.save -> the REFERENCE's PPOAgent.load (src/agents/ppo.py:433-439) on the CPU: same
+    parameters, the optimizer state accepted, and the reference network then computes the logits and values
+    our network computes on the same observation (fp32)."""
+    import sys
+    from conftest import reference_paths
+    for pth in reference_paths():
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    from agents.ppo import PPOAgent as RefAgent, PPOConfig as RefConfig
+    from bbgpu.ppo import PPOAgent
+    from bbgpu.vec_env import VectorizedBlockBlastEnv
+    torch.manual_seed(2)
+    mine = PPOAgent()
+    venv = VectorizedBlockBlastEnv(32, seed=4, output="packed")
+    from bbgpu.rollout import RolloutBuffer
+    from bbgpu.train import RolloutRunner
+    buf = RolloutBuffer(8, 32)
+    lv = RolloutRunner(venv, mine, buf, use_graph=False).run()
+    mine.update(buf, lv)                                   # so that the optimizer has state to save
+    path = str(tmp_path / "ck.pt")
+    mine.save(path)
+    theirs = RefAgent(config=RefConfig(), device=torch.device("cpu"))
+    theirs.load(path)
+    sd_m, sd_t = mine.network.state_dict(), theirs.network.state_dict()
+    assert set(sd_m) == set(sd_t)
+    for k in sd_m:
+        assert torch.equal(sd_m[k].cpu(), sd_t[k]), k
+    assert len(theirs.optimizer.state_dict()["state"]) == len(mine.optimizer.state_dict()["state"])
+    nv = VectorizedBlockBlastEnv(16, seed=8)
+    obs, _ = nv.reset()
+    mine.eval(); theirs.eval()
+    with torch.no_grad():
+        lg_t, v_t = theirs.network(torch.from_numpy(obs["board"]), torch.from_numpy(obs["pieces"]))
+        lg_m, v_m = mine.network(torch.from_numpy(obs["board"]).cuda(), torch.from_numpy(obs["pieces"]).cuda())
+    assert torch.allclose(lg_t, lg_m.cpu(), atol=2e-3, rtol=2e-3) and torch.allclose(v_t, v_m.cpu(), atol=2e-3, rtol=2e-3)
+    theirs.optimizer.zero_grad()                           # and it can keep training from the loaded state
+    a, lp, ent, val = theirs.network.get_action_and_value(torch.from_numpy(obs["board"]), torch.from_numpy(obs["pieces"]),
+                                                          torch.from_numpy(obs["action_mask"]).float())
+    (-(lp.mean()) + val.pow(2).mean()).backward()
+    theirs.optimizer.step()
+    nv.close(); venv.close()
+
+
 def test_vectorized_env_infos_match_oracle_including_terminal_observation(torch):
     """infos[i] of every step (block_blast_env.py:266-288) and, for finished episodes, the
     terminal statistics, final_score and terminal_observation (wrappers.py:97-100), against the
