@@ -149,6 +149,7 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
 
     vec_env.reset()
     use_graph = bool(ours.get("cuda_graph", True))
+    graph_update = bool(ours.get("cuda_graph_update", use_graph))   # the minibatch step (with its NCCL all-reduce) as a graph
     runner = RolloutRunner(vec_env, agent, buffer, use_graph)
     target_score = ours.get("stop_at_avg_score")              # optional early stop (score-vs-wallclock runs)
     max_wall_s = ours.get("max_wall_s")                       # optional wall-clock budget
@@ -164,7 +165,7 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
         while global_step < total_timesteps:
             last_values = runner.run()
             global_step += num_envs * rollout_steps
-            metrics = agent.update(buffer, last_values, use_graph=use_graph)
+            metrics = agent.update(buffer, last_values, use_graph=graph_update)
             num_updates += 1
             e_cnt, e_sum, e_max, e_len = runner.episode_stats()
             cnt, ssum, lsum = dist.all_reduce_scalars([e_cnt, e_sum, e_len], device=device)
