@@ -580,12 +580,22 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    def agree(count):
+        """the same block count on every rank (each block contains barriers): max over ranks"""
+        t = torch.tensor([int(count)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
     t_wall0 = time.perf_counter()
     times, k0, launched = [], W, 0
-    while len(times) < 5 or (sum(times) < args.min_seconds * 1e3 and len(times) < 2000):
+    n_blocks = 5
+    while len(times) < n_blocks:
         times.append(block(k0, K, sptr))
         k0 += K
         launched += K
+        if len(times) == 5:               # size the run from the first blocks: >= min_seconds of device time in total
+            n_blocks = agree(min(2000, max(5, int(args.min_seconds * 1e3 / _median(times)) + 1)))
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     s = stats.cpu().tolist()
@@ -649,8 +659,12 @@ def main():
         venv.reset()
         for _ in range(3):
             venv.step(venv.sample_valid_actions())
-        blocks, n_term = [], 0
-        while len(blocks) < 3 or (sum(blocks) < min_seconds and len(blocks) < 500):
+        blocks, n_term, n_blocks = [], 0, 3
+        while len(blocks) < n_blocks:
+            if len(blocks) == 3:
+                n_blocks = agree(min(500, max(3, int(min_seconds / _median(blocks)) + 1)))
+                if n_blocks == 3:
+                    break
             barrier()
             t0 = time.perf_counter()
             for _ in range(Ke):
