@@ -316,7 +316,19 @@ def kernel_rooflines(dev, peak):
     b = (768 * 2 + 36) * n
     out["K3_backward_f32"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
                               "frac_of_hbm_peak": b / t / 1e9 / peak}
-    del logits, lb, gl
+    # fused PPO loss tail (bb_ppo_loss): logits read + gradient written + 24 B mask + 7 scalars per row
+    vals, gv = torch.randn(n, device=dev), torch.empty(n, device=dev)
+    sums = torch.zeros(5, dtype=torch.float64, device=dev)
+    t = timeit(lambda: capi.ppo_loss(logits, mask, n, act, lp, g1, g2, vals, 0.2, 0.5, 0.01, gl, gv, sums))
+    b = (768 * 2 + 24 + 28) * n
+    out["ppo_loss_f32"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                           "frac_of_hbm_peak": b / t / 1e9 / peak}
+    glb = torch.empty_like(lb)
+    t = timeit(lambda: capi.ppo_loss(lb, mask, n, act, lp, g1, g2, vals, 0.2, 0.5, 0.01, glb, gv, sums))
+    b = (384 * 2 + 24 + 28) * n
+    out["ppo_loss_bf16"] = {"rows": n, "us": t * 1e6, "algorithmic_bytes": b, "achieved_GBs": b / t / 1e9,
+                            "frac_of_hbm_peak": b / t / 1e9 / peak}
+    del logits, lb, gl, glb
     # K2 obs unpack: 36 B in, 1,024 B f32 planes out (+ 192 B u8 mask) per env
     board = torch.randint(-2 ** 62, 2 ** 62, (n,), dtype=torch.int64, device=dev)
     pieces = torch.randint(0, 37, (n,), dtype=torch.int32, device=dev) * 0x010101

@@ -187,17 +187,28 @@ cudaError_t bb_launch_gather_minibatch(const int64_t* index, int64_t B, int64_t 
 
 // ------------------------------------------------------------------------------------ K3
 // 8 lanes per row, 4 rows per warp.  Lane l of a row group owns the 24 actions
-//     a(l,k,c) = 32k + 4l + c        k = 0..5, c = 0..3
+//     a(l,k,c) = 32k + 4l + c        k = 0..5, c = 0..3      (register index i = 4k + c)
 // i.e. the k-th 128-bit load of the group is one contiguous 128 B (f32) run.  Everything else
-// is per-lane arithmetic plus 3-step butterflies inside the 8-lane group:
-//   p_i = exp(z_i - m) / S            (exp2 on pre-scaled inputs)
-//   log_prob = log(clamp(p_a / sum(p), eps, 1-eps))          torch Categorical (network.py:213-225)
-//   entropy  = log S - sum_i e_i (z_i - m) / S               == -sum q log q (network.py:246-260);
-//              the reference's clamps at 1e-10 change it by < 1e-8
-// Sampling is the inverse CDF of u * sum(p) over the order (lane, k, c) — a fixed permutation
-// of the actions, so the draw is an exact categorical sample; philox.py documents the order.
+// is per-lane arithmetic plus 3-step butterflies inside the 8-lane group.  Maths (network.py:172-262):
+//   e_i = 2^((z_i - m) log2 e)        one FFMA + one MUFU per action; masked actions carry z = -1e30,
+//                                     so e_i is exactly 0 and every product with it stays finite
+//   S = sum e_i,  log p_a = (z_a - m) - log S, clamped to [log eps, log(1 - eps)]   (torch Categorical
+//                                     clamps the normalised probability, network.py:213-225)
+//   entropy  = log S - sum_i e_i (z_i - m) / S   == -sum q log q (network.py:246-260); the reference's
+//              clamps at 1e-10 change it by < 1e-8
+// Sampling is the inverse CDF of u * S over the UNNORMALISED e_i in the order (lane, k, c) — a fixed
+// permutation of the actions, so the draw is an exact categorical sample; philox.py documents the
+// order.  The lane's running sums are its local CDF; the pick is the number of entries <= the
+// threshold.  z_a of the chosen / given action is re-read from global memory (an L1 hit) instead of
+// being selected out of 24 registers.  The first version of this layout normalised all 24
+// probabilities, summed them again and selected p_a with 24 predicated moves per lane: ~700
+// instructions per lane, instruction-bound at the same 103 us for f32 and bf16 logits; this one
+// executes ~300.
 #define K3_LOG2E 1.4426950408889634f
-#define K3_DMIN (-150.0f)     // exp2(-150 * log2e) == 0 in float32: masked and hopeless actions alike
+#define K3_LN2 0.6931471805599453f
+#define K3_MASKED (-1.0e30f)   // stands in for -inf: 2^(K3_MASKED * log2e) == 0 and 0 * K3_MASKED == 0
+#define K3_LOG_EPS (-15.942385152878742f)          // log(torch.finfo(float32).eps)
+#define K3_LOG_1M_EPS (-1.1920929665620860e-07f)   // log(1 - eps)
 
 __device__ __forceinline__ float k3_ex2(float x) {      // 2^x, one MUFU (rel. error 2^-22)
     float y;
@@ -216,26 +227,21 @@ __device__ __forceinline__ float grp_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(128)
-bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
-                        uint64_t seed, uint64_t call_counter, int mode, int32_t* __restrict__ action,
-                        float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n, int64_t row_offset,
-                        const uint64_t* __restrict__ counter_dev) {
-    const int lane = threadIdx.x & 31;
-    const int l = lane & 7;                       // lane inside the row group
-    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const bool live = row_raw < n;
-    const int64_t row = live ? row_raw : n - 1;   // out-of-range groups shadow the last row, never store
-
-    float z[24];
-    uint32_t mb = 0;                              // bit (4k + c) = mask of a(l,k,c)
+// mask bits of this lane's 24 actions: bit (4k + c) = action 32k + 4l + c
+__device__ __forceinline__ uint32_t k3_lane_mask(const uint64_t* __restrict__ mask, int64_t stride, int64_t row, int l) {
+    uint32_t mb = 0;
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         const uint64_t w = __ldg(mask + (int64_t)p * stride + row);
         mb |= ((uint32_t)(w >> (4 * l)) & 0xFu) << (8 * p);
         mb |= ((uint32_t)(w >> (32 + 4 * l)) & 0xFu) << (8 * p + 4);
     }
+    return mb;
+}
+
+// this lane's 24 logits, masked ones replaced by K3_MASKED
+template <bool BF16>
+__device__ __forceinline__ void k3_load_row(const void* __restrict__ logits, int64_t row, int l, uint32_t mb, float z[24]) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         float4 v;
@@ -248,61 +254,72 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         }
         z[4 * k + 0] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w;
     }
-    float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-        z[i] = ((mb >> i) & 1u) ? z[i] : -INFINITY;               // -inf masking (network.py:175-180)
-        m = fmaxf(m, z[i]);
-    }
+    for (int i = 0; i < 24; ++i) z[i] = ((mb >> i) & 1u) ? z[i] : K3_MASKED;      // masking (network.py:175-180)
+}
+
+template <bool BF16>
+__device__ __forceinline__ float k3_logit(const void* __restrict__ logits, int64_t row, int a) {
+    if (BF16) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(logits)[row * 192 + a] << 16);
+    return reinterpret_cast<const float*>(logits)[row * 192 + a];
+}
+
+// is action a (0..191) set in the three mask planes of `row`
+__device__ __forceinline__ bool k3_action_valid(const uint64_t* __restrict__ mask, int64_t stride, int64_t row, int a) {
+    if (a < 0 || a >= 192) return false;
+    return (__ldg(mask + (int64_t)(a >> 6) * stride + row) >> (a & 63)) & 1ull;
+}
+
+// MODE 0 sample, 1 argmax, 2 evaluate the given actions; ENT: also write the masked entropy
+template <bool BF16, int MODE, bool ENT>
+__global__ void __launch_bounds__(128)
+bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
+                        uint64_t seed, uint64_t call_counter, int32_t* __restrict__ action,
+                        float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n, int64_t row_offset,
+                        const uint64_t* __restrict__ counter_dev) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & 7;                       // lane inside the row group
+    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool live = row_raw < n;
+    const int64_t row = live ? row_raw : n - 1;   // out-of-range groups shadow the last row, never store
+
+    float z[24];
+    const uint32_t mb = k3_lane_mask(mask, stride, row, l);
+    k3_load_row<BF16>(logits, row, l, mb, z);
+    float m = K3_MASKED;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) m = fmaxf(m, z[i]);
     m = grp_max(m);
-    const bool any_valid = m > -INFINITY;
-    const float mm = any_valid ? m : 0.f;
-    float s = 0.f, sz = 0.f;
+    const bool any_valid = m > 0.5f * K3_MASKED;
+    const float nm2 = any_valid ? -m * K3_LOG2E : 0.f;
+    // z[i] becomes the lane's running sum of e (its local CDF); sz2 = sum e_i d_i log2e
+    float run = 0.f, sz2 = 0.f, best = -1.f;
+    int bi = 0;
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
-        const float d = fmaxf(z[i] - mm, K3_DMIN);                 // <= 0; clamped so that 0 * d stays 0
-        const float e = k3_ex2(d * K3_LOG2E);                      // exactly 0 for masked actions
-        s += e;
-        sz = fmaf(e, d, sz);
-        z[i] = e;                                                  // z now holds exp(z - m)
+        const float d2 = fmaf(z[i], K3_LOG2E, nm2);               // (z - m) log2e <= 0
+        const float e = k3_ex2(d2);                               // exactly 0 for masked actions
+        if (ENT) sz2 = fmaf(e, d2, sz2);
+        if (MODE == 1) { if (e > best) { best = e; bi = i; } }     // first maximum = lowest action index of the lane
+        run += e;
+        z[i] = run;
     }
-    s = grp_sum(s);
-    sz = grp_sum(sz);
-    const float inv = any_valid ? __frcp_rn(s) : 0.f;
-    float ps = 0.f;                                                // sum of the rounded probabilities
-#pragma unroll
-    for (int i = 0; i < 24; ++i) { z[i] *= inv; ps += z[i]; }     // z now holds p
-    const float lane_tot = ps;
-    ps = grp_sum(ps);
+    const float lane_tot = run;
+    const float s = grp_sum(lane_tot);
 
     int act = 0;
-    float pa = 0.f;
-    if (mode == 2) {
+    if (MODE == 2) {
         act = action[row];
-        // owner lane / slot of action a: k = a / 32, l = (a % 32) / 4, c = a % 4
-        float mine = 0.f;
-        const int slot = ((act >> 5) << 2) | (act & 3);
-        const bool own = act >= 0 && act < 192 && ((act & 31) >> 2) == l;
-#pragma unroll
-        for (int i = 0; i < 24; ++i) mine += (own && i == slot) ? z[i] : 0.f;
-        pa = grp_sum(mine);
-    } else if (mode == 1) {
+    } else if (MODE == 1) {
         // argmax of probs, lowest action index on ties (torch.argmax)
-        float best = -1.f;
-        int bi = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int idx = 32 * (i >> 2) + 4 * l + (i & 3);
-            if (z[i] > best || (z[i] == best && idx < bi)) { best = z[i]; bi = idx; }
-        }
+        int idx = 32 * (bi >> 2) + 4 * l + (bi & 3);
 #pragma unroll
         for (int d = 1; d < 8; d <<= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
-        act = any_valid ? bi : 0;
-        pa = any_valid ? best : 0.f;
+        act = any_valid ? idx : 0;
     } else {
         // keyed by the GLOBAL row id (env shards on several GPUs draw independent noise) and by a call
         // counter that may live on the device (a CUDA graph replays the launch with a new value)
@@ -311,65 +328,57 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         const BBPhilox4 r = bb_philox((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)ctr,
                                       BB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-        const float t = u * ps;
-        // exclusive prefix of the lane totals inside the group
+        const float t = u * s;
+        // inclusive prefix of the lane totals inside the group
         float incl = lane_tot;
 #pragma unroll
         for (int d = 1; d < 8; d <<= 1) {
             const float o = __shfl_up_sync(0xffffffffu, incl, d, 8);
             if (l >= d) incl += o;
         }
-        const float excl = incl - lane_tot;
         // first lane whose inclusive prefix exceeds t (and that has any probability mass)
         const unsigned hit = (__ballot_sync(0xffffffffu, incl > t && lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
         const unsigned nz = (__ballot_sync(0xffffffffu, lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
         // rounding can leave t >= total: fall back to the last lane with mass
         const int L = hit ? (__ffs((int)hit) - 1) : (nz ? (31 - __clz((int)nz)) : 0);
-        // inside lane L: first element whose running sum exceeds t, else its last non-zero one;
-        // first the 4-action chunk, then the action inside it
-        float c4[6];
+        // inside the lane: the pick is the number of CDF entries <= the local threshold (masked entries
+        // repeat the previous value, so they are skipped together with it), at most its last valid one
+        const float tl = t - (incl - lane_tot);
+        int cnt = 0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c4[k] = (z[4 * k] + z[4 * k + 1]) + (z[4 * k + 2] + z[4 * k + 3]);
-        float run = excl;
-        int kc = -1, klast = 0;
-        float runc = excl, runlast = excl;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            if (c4[k] > 0.f) { klast = k; runlast = run; if (kc < 0 && run + c4[k] > t) { kc = k; runc = run; } }
-            run += c4[k];
-        }
-        if (kc < 0) { kc = klast; runc = runlast; }
-        float e4[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            e4[c] = z[c];
-#pragma unroll
-            for (int k = 1; k < 6; ++k) e4[c] = kc == k ? z[4 * k + c] : e4[c];
-        }
-        int pick = -1, lastnz = 0;
-        float ppick = 0.f, plast = 0.f, r2 = runc;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            r2 += e4[c];
-            if (e4[c] > 0.f) { lastnz = c; plast = e4[c]; if (pick < 0 && r2 > t) { pick = c; ppick = e4[c]; } }
-        }
-        if (pick < 0) { pick = lastnz; ppick = plast; }
-        pick += 4 * kc;
+        for (int i = 0; i < 24; ++i) cnt += (z[i] <= tl) ? 1 : 0;
+        const int last = 31 - __clz((int)(mb | 1u));
+        const int pick = cnt < last ? cnt : last;
         const int idx = 32 * (pick >> 2) + 4 * l + (pick & 3);
-        const int src = (lane & 24) | L;
-        act = __shfl_sync(0xffffffffu, idx, src);
-        pa = __shfl_sync(0xffffffffu, ppick, src);
-        if (!any_valid) { act = 0; pa = 0.f; }
+        act = __shfl_sync(0xffffffffu, idx, (lane & 24) | L);
+        if (!any_valid) act = 0;
     }
+    const float szt = ENT ? grp_sum(sz2) : 0.f;       // group reduction: executed by all 8 lanes
     if (live && l == 0) {
-        if (mode != 2) action[row] = act;
+        if (MODE != 2) action[row] = act;
+        const float logS = any_valid ? logf(s) : 0.f;
         if (logp_out) {
-            const float eps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
-            const float pn = any_valid ? pa / ps : 1.f;
-            logp_out[row] = logf(fminf(fmaxf(pn, eps), 1.f - eps));
+            float lp = K3_LOG_1M_EPS;             // all-masked row: p = 1 clamped (the reference would produce NaN)
+            if (any_valid) {
+                const bool ok = MODE != 2 || k3_action_valid(mask, stride, row, act);
+                const int a = ok ? act : 0;
+                lp = ok ? fmaf(k3_logit<BF16>(logits, row, a), K3_LOG2E, nm2) * K3_LN2 - logS : K3_LOG_EPS;
+                lp = fminf(fmaxf(lp, K3_LOG_EPS), K3_LOG_1M_EPS);
+            }
+            logp_out[row] = lp;
         }
-        if (ent_out) ent_out[row] = any_valid ? (logf(s) - sz * inv) : 0.f;
+        if (ENT && ent_out) ent_out[row] = any_valid ? (logS - szt * K3_LN2 / s) : 0.f;
     }
+}
+
+template <bool BF16, int MODE>
+static void k3_launch(bool ent, unsigned grid, cudaStream_t stream, const void* logits, const uint64_t* mask, int64_t stride,
+                      uint64_t seed, uint64_t call_counter, int32_t* action, float* logp, float* entropy, int64_t n,
+                      int64_t row_offset, const uint64_t* counter_dev) {
+    if (ent)
+        bb_masked_sample_kernel<BF16, MODE, true><<<grid, 128, 0, stream>>>(logits, mask, stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev);
+    else
+        bb_masked_sample_kernel<BF16, MODE, false><<<grid, 128, 0, stream>>>(logits, mask, stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev);
 }
 
 cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
@@ -378,10 +387,14 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
                                     int64_t row_offset, const uint64_t* counter_dev) {
     if (n <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n * 8 + 127) / 128);
-    if (logits_dtype == 1)
-        bb_masked_sample_kernel<true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n, row_offset, counter_dev);
-    else
-        bb_masked_sample_kernel<false><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, seed, call_counter, mode, action, logp, entropy, n, row_offset, counter_dev);
+    const bool ent = entropy != nullptr;
+#define K3_GO(BF, MD) k3_launch<BF, MD>(ent, grid, stream, logits, mask, mask_stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev)
+    if (logits_dtype == 1) {
+        if (mode == 0) K3_GO(true, 0); else if (mode == 1) K3_GO(true, 1); else K3_GO(true, 2);
+    } else {
+        if (mode == 0) K3_GO(false, 0); else if (mode == 1) K3_GO(false, 1); else K3_GO(false, 2);
+    }
+#undef K3_GO
     return cudaGetLastError();
 }
 
@@ -392,6 +405,12 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
 //   d entropy  / d z_i = -p_i (log p_i + H)
 // for valid actions i, 0 for masked ones.  Same 8-lanes-per-row layout as the forward; p is
 // recomputed from the logits (768 B read + 768 B written per row, nothing saved between passes).
+// With d_i = z_i - m, e_i = 2^(d_i log2e):
+//   dlogits_i = e_i * (c0 + c1 d_i)      c1 = -g_ent / S,  c0 = (-g_logp - g_ent (H - log S)) / S
+// i.e. FADD + FMUL + MUFU (e), FADD + FFMA (S and the entropy sum), FFMA + FMUL (gradient) per action; e_i is
+// exactly 0 for masked actions, which zeroes their gradient without a select.  The delta term of the
+// taken action is added by its owner lane with one scalar store after its vector stores (same thread,
+// program order).
 //
 // LOSS = true turns the same pass into the whole PPO loss tail (src/agents/ppo.py:366-395 +
 // network.py:210-262): with old log-probs, advantages, returns and the value
@@ -413,43 +432,34 @@ bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __res
                           const float* __restrict__ g_ent, void* __restrict__ dlogits, int64_t n, BBPpoLossArgs L) {
     const int lane = threadIdx.x & 31;
     const int l = lane & 7;
-    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    // Warps walk the rows grid-stride, four rows per warp and trip (the loop bound is warp-uniform: the
+    // shuffles below need all 32 lanes).  LOSS launches cap the grid (bb_launch_ppo_loss), so the five metric
+    // sums leave each warp ONCE, after its last row: with one atomic set per four rows the 131,072 warps of
+    // a 524,288-row call queued 655 k double atomics on five addresses and the kernel took 874 us, 15x its
+    // memory time.
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;       // metric partial sums of this lane (LOSS)
+    for (int64_t r0 = warp0 * 4; r0 < n; r0 += n_warps * 4) {
+    const int64_t row_raw = r0 + (lane >> 3);
     const bool live = row_raw < n;
     const int64_t row = live ? row_raw : n - 1;
-    float z[24];
-    uint32_t mb = 0;
+    float z[24], e[24];
+    const uint32_t mb = k3_lane_mask(mask, stride, row, l);
+    k3_load_row<BF16>(logits, row, l, mb, z);
+    float m = K3_MASKED;
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        const uint64_t w = __ldg(mask + (int64_t)p * stride + row);
-        mb |= ((uint32_t)(w >> (4 * l)) & 0xFu) << (8 * p);
-        mb |= ((uint32_t)(w >> (32 + 4 * l)) & 0xFu) << (8 * p + 4);
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        float4 v;
-        if (BF16) {
-            const uint2 h = reinterpret_cast<const uint2*>(logits)[row * 48 + k * 8 + l];
-            v.x = __uint_as_float(h.x << 16); v.y = __uint_as_float(h.x & 0xFFFF0000u);
-            v.z = __uint_as_float(h.y << 16); v.w = __uint_as_float(h.y & 0xFFFF0000u);
-        } else {
-            v = reinterpret_cast<const float4*>(logits)[row * 48 + k * 8 + l];
-        }
-        z[4 * k + 0] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w;
-    }
-    float m = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 24; ++i) m = fmaxf(m, ((mb >> i) & 1u) ? z[i] : -INFINITY);
+    for (int i = 0; i < 24; ++i) m = fmaxf(m, z[i]);
     m = grp_max(m);
-    const bool any_valid = m > -INFINITY;
+    const bool any_valid = m > 0.5f * K3_MASKED;
+    const float mm = any_valid ? m : 0.f;
     float s = 0.f, sz = 0.f;
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
-        const bool ok = (mb >> i) & 1u;
-        const float d = ok ? z[i] - m : 0.f;
-        const float e = ok ? exp2f(d * K3_LOG2E) : 0.f;
-        s += e;
-        sz = fmaf(e, d, sz);
-        z[i] = d;                                   // keep z - m (0 where masked)
+        z[i] -= mm;                                // d = z - m: exactly 0 for the maximum (a one-action row gets an exactly zero gradient, like torch)
+        e[i] = k3_ex2(z[i] * K3_LOG2E);            // exactly 0 where masked
+        s += e[i];
+        sz = fmaf(e[i], z[i], sz);
     }
     s = grp_sum(s);
     sz = grp_sum(sz);
@@ -457,17 +467,14 @@ bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __res
     const float logS = any_valid ? logf(s) : 0.f;
     const float H = logS - sz * inv;                // masked entropy
     const int act = action[row];
-    const int slot = ((act >> 5) << 2) | (act & 3);
-    const bool own = act >= 0 && act < 192 && ((act & 31) >> 2) == l;
-    // p_a for the clamp indicator
-    float mine = 0.f;
-#pragma unroll
-    for (int i = 0; i < 24; ++i) mine += (own && i == slot && ((mb >> i) & 1u)) ? exp2f(z[i] * K3_LOG2E) * inv : 0.f;
-    const float pa = grp_sum(mine);
+    const bool act_ok = any_valid && k3_action_valid(mask, stride, row, act);
+    // z - m and p of the taken action (0 when it is masked / out of range)
+    const float da = act_ok ? k3_logit<BF16>(logits, row, act) - mm : 0.f;
+    const float pa = act_ok ? k3_ex2(da * K3_LOG2E) * inv : 0.f;
     const float eps = 1.1920928955078125e-07f;
     float g1, g2;
     if (LOSS) {
-        const float logp = any_valid ? logf(fminf(fmaxf(pa, eps), 1.f - eps)) : 0.f;
+        const float logp = any_valid ? fminf(fmaxf(act_ok ? da - logS : K3_LOG_EPS, K3_LOG_EPS), K3_LOG_1M_EPS) : 0.f;
         const float lr = logp - L.old_logp[row];
         const float ratio = expf(lr);
         const float A = L.adv[row];
@@ -478,14 +485,46 @@ bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __res
         const float dv = L.value[row] - L.ret[row];
         g1 = (through && pa >= eps && pa <= 1.f - eps) ? -A * ratio * L.inv_n : 0.f;
         g2 = -L.entropy_coef * L.inv_n;
-        // per-row metric terms: lane 0 of each 8-lane group holds them, summed per warp, one
-        // atomic per warp and sum
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+        // per-row metric terms: lane 0 of each 8-lane group accumulates them over the warp's rows
         if (live && l == 0) {
             L.dvalue[row] = 2.f * L.value_coef * dv * L.inv_n;
-            t0 = -fminf(s1, s2); t1 = dv * dv; t2 = H; t3 = (ratio - 1.f) - lr;
-            t4 = fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
+            t0 -= fminf(s1, s2); t1 = fmaf(dv, dv, t1); t2 += H; t3 += (ratio - 1.f) - lr;
+            t4 += fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
         }
+    } else {
+        g1 = (pa >= eps && pa <= 1.f - eps) ? g_logp[row] : 0.f;
+        g2 = g_ent ? g_ent[row] : 0.f;
+    }
+    // dlogits_i = -g1 p_i - g2 p_i (log p_i + H),  log p_i = d_i - log S
+    const float c1 = -g2 * inv;
+    const float c0 = (-g1 - g2 * (H - logS)) * inv;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) e[i] *= fmaf(z[i], c1, c0);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (BF16) {
+                const __nv_bfloat162 a = __floats2bfloat162_rn(e[4 * k], e[4 * k + 1]);
+                const __nv_bfloat162 b = __floats2bfloat162_rn(e[4 * k + 2], e[4 * k + 3]);
+                uint2 h;
+                h.x = *reinterpret_cast<const uint32_t*>(&a);
+                h.y = *reinterpret_cast<const uint32_t*>(&b);
+                reinterpret_cast<uint2*>(dlogits)[row * 48 + k * 8 + l] = h;
+            } else {
+                reinterpret_cast<float4*>(dlogits)[row * 48 + k * 8 + l] =
+                    make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+            }
+        }
+        // the delta term of the taken action, by the lane that owns (and has just stored) that element
+        if (act_ok && g1 != 0.f && ((act & 31) >> 2) == l) {
+            const float ga = k3_ex2(da * K3_LOG2E) * fmaf(da, c1, c0) + g1;
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(dlogits)[row * 192 + act] = __float2bfloat16_rn(ga);
+            else reinterpret_cast<float*>(dlogits)[row * 192 + act] = ga;
+        }
+    }
+    }   // rows of this warp
+    if (LOSS) {
+        // lanes 0, 8, 16, 24 hold the partial sums: fold them, one atomic per warp and sum
 #pragma unroll
         for (int d = 8; d < 32; d <<= 1) {
             t0 += __shfl_xor_sync(0xffffffffu, t0, d); t1 += __shfl_xor_sync(0xffffffffu, t1, d);
@@ -495,34 +534,6 @@ bb_masked_head_bwd_kernel(const void* __restrict__ logits, const uint64_t* __res
         if (lane == 0) {
             atomicAdd(&L.sums[0], (double)t0); atomicAdd(&L.sums[1], (double)t1); atomicAdd(&L.sums[2], (double)t2);
             atomicAdd(&L.sums[3], (double)t3); atomicAdd(&L.sums[4], (double)t4);
-        }
-    } else {
-        g1 = (pa >= eps && pa <= 1.f - eps) ? g_logp[row] : 0.f;
-        g2 = g_ent ? g_ent[row] : 0.f;
-    }
-    float out[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) {
-        const bool ok = (mb >> i) & 1u;
-        const float p = ok ? exp2f(z[i] * K3_LOG2E) * inv : 0.f;
-        const float logp = z[i] - logS;             // log p_i for valid i
-        float g = -g1 * p - g2 * p * (logp + H);
-        if (own && i == slot) g += g1;
-        out[i] = ok ? g : 0.f;
-    }
-    if (!live) return;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        if (BF16) {
-            const __nv_bfloat162 a = __floats2bfloat162_rn(out[4 * k], out[4 * k + 1]);
-            const __nv_bfloat162 b = __floats2bfloat162_rn(out[4 * k + 2], out[4 * k + 3]);
-            uint2 h;
-            h.x = *reinterpret_cast<const uint32_t*>(&a);
-            h.y = *reinterpret_cast<const uint32_t*>(&b);
-            reinterpret_cast<uint2*>(dlogits)[row * 48 + k * 8 + l] = h;
-        } else {
-            reinterpret_cast<float4*>(dlogits)[row * 48 + k * 8 + l] =
-                make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
         }
     }
 }
@@ -545,7 +556,10 @@ cudaError_t bb_launch_ppo_loss(const void* logits, int dtype, const uint64_t* ma
                                const float* value, float clip, float value_coef, float entropy_coef,
                                void* dlogits, float* dvalue, double* sums, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n * 8 + 127) / 128);
+    // one wave of 5 blocks per SM at most: every warp then walks n / 11,840 row quads and issues its five
+    // atomics once, after its last row (float partial sums over at most a few hundred rows per lane)
+    const int64_t want = (n * 8 + 127) / 128;
+    const unsigned grid = (unsigned)(want < 148 * 5 ? want : 148 * 5);
     const BBPpoLossArgs L = {old_logp, adv, ret, value, dvalue, sums, clip, value_coef, entropy_coef, 1.0f / (float)n};
     if (dtype == 1)
         bb_masked_head_bwd_kernel<true, true><<<grid, 128, 0, stream>>>(logits, mask, mask_stride, action, nullptr, nullptr, dlogits, n, L);

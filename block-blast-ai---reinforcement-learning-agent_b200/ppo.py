@@ -75,7 +75,10 @@ class PPOAgent:
                                           fused=self.device.type == "cuda", capturable=self.device.type == "cuda")
         self._graph = None
         self.scheduler = None
-        self.bucket = dist.FlatGradBucket(self.network.parameters())
+        # gradients of the FC encoder + heads (everything after the convolution stack in parameter order) are
+        # reduced while backward is still in the convolutions
+        n_conv = len(list(self.network.conv_encoder.parameters()))
+        self.bucket = dist.FlatGradBucket(self.network.parameters(), early_from=n_conv)
 
     # ------------------------------------------------------------------ helpers
     def _autocast(self):

@@ -104,7 +104,20 @@ def _gloo_worker(rank, world, port, out):
     bucket.all_reduce_mean()                                  # C1: one flat all-reduce, averaged
     tot = dist.all_reduce_scalars([rank + 1.0, 10.0 * (rank + 1)], device="cpu")
     mx = dist.all_reduce_scalars([rank + 1.0], op="max", device="cpu")
-    out.put((rank, w0.tolist(), local.tolist(), bucket.flat.tolist(), tot, mx, dist.shard(9)))
+    # two-slice mode: the last Linear's gradients (early slice) are reduced from a post-accumulate hook while
+    # backward is still running, the rest afterwards; two consecutive steps give the plain mean both times
+    lin2 = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    dist.broadcast_module(lin2)
+    b2 = dist.FlatGradBucket(lin2.parameters(), early_from=2)
+    early = []
+    for step in range(2):
+        b2.zero()
+        (lin2(x * (step + 1)).sum() * (rank + 2)).backward()
+        loc2 = b2.flat.clone()
+        fired = b2._work is not None
+        b2.all_reduce_mean()
+        early.append((fired, loc2.tolist(), b2.flat.tolist()))
+    out.put((rank, w0.tolist(), local.tolist(), bucket.flat.tolist(), tot, mx, dist.shard(9), early))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -120,7 +133,10 @@ def test_two_rank_gloo_gradient_bucket_and_scalars():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, w0, l0, a0, t0, m0, s0), (r1, w1, l1, a1, t1, m1, s1) = res
+    (r0, w0, l0, a0, t0, m0, s0, e0), (r1, w1, l1, a1, t1, m1, s1, e1) = res
+    for (f0, loc0, red0), (f1, loc1, red1) in zip(e0, e1):       # overlapped two-slice reduction
+        assert f0 and f1                                        # the early slice went out from the hook
+        assert np.allclose(red0, red1) and np.allclose(red0, (np.array(loc0) + np.array(loc1)) / 2) and loc0 != loc1
     assert w0 == w1                                            # broadcast worked
     assert np.allclose(a0, a1) and np.allclose(a0, (np.array(l0) + np.array(l1)) / 2)
     assert l0 != l1

@@ -13,6 +13,7 @@ import torch
 from bbgpu import capi
 
 dev = "cuda"
+REP = int(os.environ.get("BB_REPS", "2"))        # launches per kernel (1 keeps an ncu --set full report small)
 n = 262144
 envs = [capi.EnvHandle(n, 42, b * n) for b in range(8)]
 outs = [dict(a=torch.zeros(n, dtype=torch.int32, device=dev), r=torch.zeros(n, device=dev),
@@ -21,12 +22,12 @@ st = torch.zeros(8, dtype=torch.int64, device=dev)
 for e, o in zip(envs, outs):
     e.step_random(64, None, None, None, o["m"])
 torch.cuda.synchronize()
-for k in range(8):                                            # K1 random policy (the bench kernel), L2-cold rotation
+for k in range(8 if REP > 1 else 3):                          # K1 random policy (the bench kernel), L2-cold rotation
     o = outs[k]
     envs[k].step_random(1, o["a"], o["r"], o["t"], o["m"], st, o["m"])
 board = torch.zeros(n, dtype=torch.int64, device=dev)
 pieces = torch.zeros(n, dtype=torch.int32, device=dev)
-for k in range(2):                                            # K1 given actions, all outputs (the PPO collect form)
+for k in range(REP):                                          # K1 given actions, all outputs (the PPO collect form)
     o = outs[k]
     envs[k].step(o["a"], o["r"], o["t"], o["m"], None, None, None, board, pieces, st)
 T, N = 128, 262144
@@ -35,7 +36,7 @@ d = (torch.rand(T, N, device=dev) < 0.07).float()
 lv = torch.randn(N, device=dev)
 adv, ret = torch.empty_like(rw), torch.empty_like(rw)
 mom = torch.zeros(2, dtype=torch.float64, device=dev)
-for _ in range(2):
+for _ in range(REP):
     capi.gae(rw, v, d, lv, 0.99, 0.95, adv, ret, mom)          # K4
 del rw, v, d, adv, ret
 nn = 524288
@@ -44,19 +45,19 @@ mask = torch.randint(-2 ** 62, 2 ** 62, (3, nn), dtype=torch.int64, device=dev) 
 act = torch.empty(nn, dtype=torch.int32, device=dev)
 lp, en = torch.empty(nn, device=dev), torch.empty(nn, device=dev)
 lb = logits.bfloat16()
-for _ in range(2):
+for _ in range(REP):
     capi.masked_sample(logits, mask, nn, 1, 1, 0, act, lp, en)  # K3 f32 sample
-for _ in range(2):
+for _ in range(REP):
     capi.masked_sample(lb, mask, nn, 1, 1, 0, act, lp, en)      # K3 bf16 sample
 gl = torch.empty_like(logits)
 g1, g2 = torch.randn(nn, device=dev), torch.randn(nn, device=dev)
-for _ in range(2):
+for _ in range(REP):
     capi.masked_head_backward(logits, mask, nn, act, g1, g2, gl)   # K3 backward
 vals = torch.randn(nn, device=dev)
 gv = torch.empty(nn, device=dev)
 sums = torch.zeros(5, dtype=torch.float64, device=dev)
 glb = torch.empty_like(lb)
-for _ in range(2):
+for _ in range(REP):
     capi.ppo_loss(lb, mask, nn, act, lp, g1, g2, vals, 0.2, 0.5, 0.01, glb, gv, sums)   # fused PPO loss tail (bf16 logits)
 del logits, gl, lb, glb
 b64 = torch.randint(-2 ** 62, 2 ** 62, (nn,), dtype=torch.int64, device=dev)
@@ -64,9 +65,9 @@ pcs = torch.randint(0, 37, (nn,), dtype=torch.int32, device=dev) * 0x010101
 obs = torch.empty((nn, 4, 8, 8), device=dev)
 obs16 = torch.empty((nn, 4, 8, 8), dtype=torch.bfloat16, device=dev)
 dense = torch.empty((nn, 192), dtype=torch.uint8, device=dev)
-for _ in range(2):
+for _ in range(REP):
     capi.unpack_obs(b64, pcs, mask, nn, obs=obs, mask_dense=dense, n=nn)     # K2 f32 + dense mask
-for _ in range(2):
+for _ in range(REP):
     capi.unpack_obs(b64, pcs, mask, nn, obs=obs16, n=nn)                       # K2 bf16
 # minibatch gather (RolloutBuffer.get_samples): 32,768 random samples of a T=16 x N=131,072 buffer
 Tg, Ng, B = 16, 131072, 32768
@@ -80,7 +81,7 @@ ms = torch.tensor([0.0, 1.0], device=dev)
 o = dict(obs=torch.empty((B, 4, 8, 8), device=dev), mask=torch.empty((3, B), dtype=torch.int64, device=dev),
          actions=torch.empty(B, dtype=torch.int32, device=dev), logp=torch.empty(B, device=dev), adv=torch.empty(B, device=dev),
          ret=torch.empty(B, device=dev))
-for _ in range(2):
+for _ in range(REP):
     capi.gather_minibatch(idx, Ng, gb, gp, gm, ga, gf[0], gf[1], gf[2], ms, o["obs"], o["mask"], o["actions"], o["logp"],
                           o["adv"], o["ret"])
 del gb, gp, gm, ga, gf
@@ -93,9 +94,9 @@ rm, rv = torch.zeros(ch, device=dev), torch.ones(ch, device=dev)
 sm, sr = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
 dg, db = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
 ws = torch.empty(capi.bn_workspace_size(ch), device=dev)
-for _ in range(2):
+for _ in range(REP):
     capi.bn_relu_forward(x, skip, gamma, beta, None, rm, rv, 0.1, 1e-5, True, y, sm, sr, ws, rows, ch)
-for _ in range(2):
+for _ in range(REP):
     capi.bn_relu_backward(x, y, dy, gamma, sm, sr, dx, dsk, dg, db, ws, rows, ch)
 torch.cuda.synchronize()
 print("ok")
