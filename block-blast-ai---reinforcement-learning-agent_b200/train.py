@@ -125,8 +125,15 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
         # gradient all-reduces per epoch (a hang), and unequal weights in the gradient mean
         raise ValueError("training.num_envs (%d) must be divisible by the number of GPUs (%d)" % (num_envs, world))
     offset, n_local = dist.shard(num_envs)
+    # b200.stream_period = P: env g draws its pieces from stream g mod P, i.e. the job plays num_envs / P copies of
+    # the same P piece streams (with reseed_on_reset: the reference's 64 fixed games, several trajectories of each
+    # per update); the action-sampling noise stays keyed by the true global env id, so the copies explore differently
+    period = int(ours.get("stream_period", 0) or 0)
+    if period and (period % n_local or num_envs % period):
+        raise ValueError("b200.stream_period (%d) must be a multiple of the envs per GPU (%d) and divide num_envs" % (period, n_local))
     vec_env = VectorizedBlockBlastEnv(n_local, seed=seed, reward_config=rew_c or None, output="packed",
-                                      global_env_offset=offset, reseed_on_reset=bool(ours.get("reseed_on_reset", False)))
+                                      global_env_offset=offset % period if period else offset,
+                                      reseed_on_reset=bool(ours.get("reseed_on_reset", False)))
     agent = PPOAgent(PPOConfig(
         learning_rate=ppo_c.get("learning_rate", 3e-4), gamma=ppo_c.get("gamma", 0.99),
         gae_lambda=ppo_c.get("gae_lambda", 0.95), clip_epsilon=ppo_c.get("clip_epsilon", 0.2),
