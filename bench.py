@@ -37,13 +37,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_LAUNCH = 12.63e6 + 0.05e6   # measured by ncu for one 262,144-env launch (see TRAFFIC_SOURCE)
+NCU_DRAM_BYTES_PER_LAUNCH = 18.9e6 + 0.1e6   # measured by ncu for one 262,144-env launch (see TRAFFIC_SOURCE)
 TRAFFIC_SOURCE = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                  "(profiles/r1_k1_final_ncu_summary.txt); reads are the 12.6 MB of state, the "
-                  "21 MB of outputs + state write-back were still in the 126 MB L2 when the capture ended")
-BOUND_NOTE = ("integer-issue bound, not HBM bound: ALU pipe 63% busy while an SM is active, 28.9 M warp instructions, "
-              "21.9 of 32 lanes active per instruction (ncu); a lone launch leaves SMs idle while its longest warps drain "
-              "(SMs active 78% of the launch), which the second stream fills")
+                  "(profiles/r2_kernels_ncu_summary.json, bb_step_kernel<1, 0>); reads are the 12.6 MB of state + the 6.3 MB "
+                  "mask of the previous step, the 21 MB of outputs + state write-back were still in the 126 MB L2 when the "
+                  "capture ended")
+BOUND_NOTE = ("integer-issue bound, not HBM bound: ALU pipe 62% busy while an SM is active, 27.9 M warp instructions, "
+              "21.6 of 32 lanes active per instruction (ncu); a lone launch leaves SMs idle while its longest warps drain "
+              "(SMs active 76% of the launch; 95% inside a 64-step launch), which the second stream fills")
 ALGO_BYTES_PER_ENV_STEP = 129          # SURVEY.md §8d / DESIGN.md: 48 R + 48 W + 4 + 4 + 1 + 24
 STATE_BYTES, OUT_BYTES = 48, 33
 METRIC = "env_steps_per_sec"
