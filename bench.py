@@ -364,8 +364,12 @@ def kernel_rooflines(dev, peak):
     b = 8 * rows * ch * 2
     out["BN_relu_residual_backward_bf16"] = {"rows": rows, "channels": ch, "us": t * 1e6, "algorithmic_bytes": b,
                                              "achieved_GBs": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / peak}
+    # layers without a residual input: the ReLU mask is recomputed from x, y is not read (x, dy twice; dx written)
+    t = timeit(lambda: capi.bn_relu_backward_no_skip(x, dy, gamma, beta, sm, sr, dx, dg, db, ws, rows, ch))
+    b = 5 * rows * ch * 2
+    out["BN_relu_backward_no_skip_bf16"] = {"rows": rows, "channels": ch, "us": t * 1e6, "algorithmic_bytes": b,
+                                            "achieved_GBs": b / t / 1e9, "frac_of_hbm_peak": b / t / 1e9 / peak}
     return out
-
 
 
 FWD_FLOP_PER_SAMPLE = 113.05e6          # BlockBlastNetwork forward

@@ -84,6 +84,7 @@ def lib():
     L.bb_bn_workspace_size.argtypes = [C.c_int]
     L.bb_bn_relu_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, i64, C.c_int, vp]
     L.bb_bn_relu_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp]
+    L.bb_bn_relu_backward_no_skip.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp]
     L.bb_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, i64, i64, vp]
     if L.bb_version() != ABI_VERSION:
         raise BBGpuError("libbbgpu.so ABI %d != expected %d" % (L.bb_version(), ABI_VERSION))
@@ -342,6 +343,13 @@ def bn_relu_backward(x, y, grad_y, gamma, save_mean, save_rstd, grad_x, grad_ski
     check(lib().bb_bn_relu_backward(ptr(x), ptr(y), ptr(grad_y), ptr(gamma), ptr(save_mean), ptr(save_rstd), ptr(grad_x),
                                     ptr(grad_skip), ptr(grad_gamma), ptr(grad_beta), ptr(workspace), int(rows), int(channels),
                                     current_stream()))
+
+
+def bn_relu_backward_no_skip(x, grad_y, gamma, beta, save_mean, save_rstd, grad_x, grad_gamma, grad_beta, workspace, rows,
+                             channels):
+    check(lib().bb_bn_relu_backward_no_skip(ptr(x), ptr(grad_y), ptr(gamma), ptr(beta), ptr(save_mean), ptr(save_rstd),
+                                            ptr(grad_x), ptr(grad_gamma), ptr(grad_beta), ptr(workspace), int(rows),
+                                            int(channels), current_stream()))
 
 
 def gae(rewards, values, dones, last_values, gamma, lam, adv, ret, moments=None):

@@ -31,6 +31,11 @@ __device__ __forceinline__ BF8 bn_unpack(const uint4 q) {
     return r;
 }
 
+// the affine pair of the forward pass, y = relu(x * scale + shift): ONE definition, because the backward pass of
+// layers without a residual input recomputes the ReLU mask from x with it instead of reading y back
+__device__ __forceinline__ float bn_scale(float gamma, float rstd) { return __fmul_rn(gamma, rstd); }
+__device__ __forceinline__ float bn_shift(float beta, float mean, float scale) { return __fmaf_rn(-mean, scale, beta); }
+
 __device__ __forceinline__ uint32_t bn_pack2(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -46,20 +51,26 @@ __device__ __forceinline__ uint4 bn_pack(const BF8& r) {
 // kernel adds the partials in a fixed order, so results are bit-reproducible).
 //   MODE 0: sum x, sum x^2                                  (forward statistics)
 //   MODE 1: sum g, sum g * xhat, g = dy * [y > 0]           (backward reductions)
+//   MODE 2: the same with the ReLU mask recomputed from x, [x * scale + shift > 0] with the forward's own
+//           scale / shift expressions — layers without a residual input do not need y read back at all
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bb_bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ part,
-                    int64_t M, int C) {
+                    int64_t M, int C, const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr) {
     extern __shared__ float sh[];                      // [R][2][C]
     const int G = C >> 3, R = BN_THREADS / G;
     const int g = threadIdx.x % G, r0 = threadIdx.x / G;
-    float a[8], b[8], mu[8], rs[8];
+    float a[8], b[8], mu[8], rs[8], sc[8], sf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a[k] = 0.f; b[k] = 0.f; mu[k] = 0.f; rs[k] = 1.f; }
-    if (MODE == 1) {
+    if (MODE >= 1) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { mu[k] = mean[g * 8 + k]; rs[k] = rstd[g * 8 + k]; }
+    }
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sc[k] = bn_scale(gamma[g * 8 + k], rs[k]); sf[k] = bn_shift(beta[g * 8 + k], mu[k], sc[k]); }
     }
     if (r0 < R) {
         for (int64_t row = (int64_t)blockIdx.x * R + r0; row < M; row += (int64_t)gridDim.x * R) {
@@ -67,12 +78,20 @@ bb_bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
             if (MODE == 0) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { a[k] += xv.v[k]; b[k] = fmaf(xv.v[k], xv.v[k], b[k]); }
-            } else {
+            } else if (MODE == 1) {
                 const BF8 yv = bn_unpack(__ldg(y + row * G + g));
                 const BF8 dv = bn_unpack(__ldg(dy + row * G + g));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float gk = yv.v[k] > 0.f ? dv.v[k] : 0.f;
+                    a[k] += gk;
+                    b[k] = fmaf(gk, (xv.v[k] - mu[k]) * rs[k], b[k]);
+                }
+            } else {
+                const BF8 dv = bn_unpack(__ldg(dy + row * G + g));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gk = fmaf(xv.v[k], sc[k], sf[k]) > 0.f ? dv.v[k] : 0.f;
                     a[k] += gk;
                     b[k] = fmaf(gk, (xv.v[k] - mu[k]) * rs[k], b[k]);
                 }
@@ -133,9 +152,9 @@ __global__ void bb_bn_finalize_fwd_kernel(const float* __restrict__ part, int nb
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mu + (pre_bias ? pre_bias[c] : 0.f));
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
-    const float sc = gamma[c] * rstd;
+    const float sc = bn_scale(gamma[c], rstd);
     scale[c] = sc;
-    shift[c] = beta[c] - (float)mu * sc;
+    shift[c] = bn_shift(beta[c], (float)mu, sc);
 }
 
 // eval mode: the affine pair from the running statistics
@@ -204,19 +223,21 @@ __global__ void bb_bn_finalize_bwd_kernel(const float* __restrict__ part, int nb
     c2[c] = (float)(q / (double)M);
 }
 
+template <bool NOY>      // NOY: ReLU mask recomputed from x (no residual input), y is not read
 __global__ void __launch_bounds__(BN_THREADS)
 bb_bn_dx_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
                 const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                 const float* __restrict__ c1, const float* __restrict__ c2, uint4* __restrict__ dx,
-                uint4* __restrict__ dskip, int64_t M, int C) {
+                uint4* __restrict__ dskip, int64_t M, int C, const float* __restrict__ beta = nullptr) {
     const int G = C >> 3, R = BN_THREADS / G;
     const int g = threadIdx.x % G, r0 = threadIdx.x / G;
     if (r0 >= R) return;
-    float mu[8], rs[8], sc[8], k1[8], k2[8];
+    float mu[8], rs[8], sc[8], k1[8], k2[8], sf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = g * 8 + k;
-        mu[k] = mean[c]; rs[k] = rstd[c]; sc[k] = gamma[c] * rs[k]; k1[k] = c1[c]; k2[k] = c2[c];
+        mu[k] = mean[c]; rs[k] = rstd[c]; sc[k] = bn_scale(gamma[c], rs[k]); k1[k] = c1[c]; k2[k] = c2[c];
+        sf[k] = NOY ? bn_shift(beta[c], mu[k], sc[k]) : 0.f;
     }
     const int64_t stride = (int64_t)gridDim.x * R;
     for (int64_t row = (int64_t)blockIdx.x * R + r0; row < M; row += 2 * stride) {
@@ -224,17 +245,20 @@ bb_bn_dx_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int64_t rr = row + u * stride;
-            if (rr < M) { xq[u] = __ldg(x + rr * G + g); yq[u] = __ldg(y + rr * G + g); dq[u] = __ldg(dy + rr * G + g); }
+            if (rr < M) { xq[u] = __ldg(x + rr * G + g); if (!NOY) yq[u] = __ldg(y + rr * G + g); dq[u] = __ldg(dy + rr * G + g); }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int64_t rr = row + u * stride;
             if (rr < M) {
-                const BF8 xv = bn_unpack(xq[u]), yv = bn_unpack(yq[u]), dv = bn_unpack(dq[u]);
+                const BF8 xv = bn_unpack(xq[u]), dv = bn_unpack(dq[u]);
+                BF8 yv;
+                if (!NOY) yv = bn_unpack(yq[u]);
                 BF8 gv, ov;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    gv.v[k] = yv.v[k] > 0.f ? dv.v[k] : 0.f;
+                    const bool on = NOY ? fmaf(xv.v[k], sc[k], sf[k]) > 0.f : yv.v[k] > 0.f;
+                    gv.v[k] = on ? dv.v[k] : 0.f;
                     ov.v[k] = sc[k] * (gv.v[k] - k1[k] - (xv.v[k] - mu[k]) * rs[k] * k2[k]);
                 }
                 dx[rr * G + g] = bn_pack(ov);
@@ -287,7 +311,8 @@ cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* 
 
 cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma,
                                   const float* save_mean, const float* save_rstd, void* dx, void* dskip,
-                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream) {
+                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream,
+                                  const float* beta) {
     const int grid = bn_grid();
     float* part = workspace;
     float* c1 = workspace + (size_t)grid * 2 * C;
@@ -295,11 +320,21 @@ cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, 
     const int R = BN_THREADS / (C >> 3);
     const int64_t need = (M + R - 1) / R;
     const int g = (int)(need < grid ? need : grid);
-    bb_bn_reduce_kernel<1><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
-        (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, part, M, C);
+    const bool noy = y == nullptr;        // no residual input: the mask comes from x (needs beta)
+    if (noy)
+        bb_bn_reduce_kernel<2><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
+            (const uint4*)x, nullptr, (const uint4*)dy, save_mean, save_rstd, part, M, C, gamma, beta);
+    else
+        bb_bn_reduce_kernel<1><<<g, BN_THREADS, (size_t)R * 2 * C * sizeof(float), stream>>>(
+            (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, part, M, C);
     bb_bn_finalize_bwd_kernel<<<C, BN_FIN_THREADS, 0, stream>>>(part, g, M, C, dgamma, dbeta, c1, c2);
     const int64_t need2 = (need + 1) / 2;
-    bb_bn_dx_kernel<<<(int)(need2 < grid ? (need2 > 0 ? need2 : 1) : grid), BN_THREADS, 0, stream>>>(
-        (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, gamma, c1, c2, (uint4*)dx, (uint4*)dskip, M, C);
+    const int gdx = (int)(need2 < grid ? (need2 > 0 ? need2 : 1) : grid);
+    if (noy)
+        bb_bn_dx_kernel<true><<<gdx, BN_THREADS, 0, stream>>>(
+            (const uint4*)x, nullptr, (const uint4*)dy, save_mean, save_rstd, gamma, c1, c2, (uint4*)dx, (uint4*)dskip, M, C, beta);
+    else
+        bb_bn_dx_kernel<false><<<gdx, BN_THREADS, 0, stream>>>(
+            (const uint4*)x, (const uint4*)y, (const uint4*)dy, save_mean, save_rstd, gamma, c1, c2, (uint4*)dx, (uint4*)dskip, M, C);
     return cudaGetLastError();
 }

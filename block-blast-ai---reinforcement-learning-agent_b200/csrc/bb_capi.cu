@@ -534,6 +534,18 @@ int bb_bn_relu_backward(const void* x, const void* y, const void* grad_y, const 
     return 0;
 }
 
+int bb_bn_relu_backward_no_skip(const void* x, const void* grad_y, const float* gamma, const float* beta,
+                                const float* save_mean, const float* save_rstd, void* grad_x, float* grad_gamma,
+                                float* grad_beta, float* workspace, int64_t rows, int channels, void* stream) {
+    if (bn_check(rows, channels)) return -1;
+    if (rows == 0) return 0;
+    if (!x || !grad_y || !gamma || !beta || !save_mean || !save_rstd || !grad_x || !grad_gamma || !grad_beta || !workspace)
+        return fail(-1, "bb_bn_relu_backward_no_skip: NULL array");
+    BB_CUDA(bb_launch_bn_relu_bwd(x, nullptr, grad_y, gamma, save_mean, save_rstd, grad_x, nullptr, grad_gamma, grad_beta, workspace,
+                                  rows, channels, (cudaStream_t)stream, beta), "bb_bn_relu_backward_no_skip launch");
+    return 0;
+}
+
 int bb_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
            double gamma, double lam, float* adv, float* ret, double* moments, int64_t T, int64_t N, void* stream) {
     if (T < 0 || N < 0) return fail(-1, "bb_gae: negative size");

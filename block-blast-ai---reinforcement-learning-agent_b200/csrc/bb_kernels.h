@@ -76,4 +76,5 @@ cudaError_t bb_launch_bn_relu_fwd(const void* x, const void* skip, const float* 
                                   cudaStream_t stream);
 cudaError_t bb_launch_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma,
                                   const float* save_mean, const float* save_rstd, void* dx, void* dskip,
-                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream);
+                                  float* dgamma, float* dbeta, float* workspace, int64_t M, int C, cudaStream_t stream,
+                                  const float* beta = nullptr);   // y == NULL: ReLU mask recomputed from x (needs beta)

@@ -48,21 +48,29 @@ class FusedBNReLU(torch.autograd.Function):
         pb = None if pre_bias is None else pre_bias.detach().float().contiguous()
         capi.bn_relu_forward(x, skip, weight, bias, pb, running_mean, running_var, momentum, eps, training, y,
                              save_mean, save_rstd, _bn_workspace(c, x.device), rows, c)
-        ctx.save_for_backward(x, y, weight, save_mean, save_rstd)
         ctx.has_skip = skip is not None
+        # without a residual input the ReLU mask is recomputed from x in backward: y need not be kept for it
+        if ctx.has_skip:
+            ctx.save_for_backward(x, y, weight, save_mean, save_rstd)
+        else:
+            ctx.save_for_backward(x, bias.detach(), weight, save_mean, save_rstd)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        x, y, weight, save_mean, save_rstd = ctx.saved_tensors
+        x, y_or_beta, weight, save_mean, save_rstd = ctx.saved_tensors
         n, c, h, w = x.shape
         grad_y = grad_y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         grad_x = torch.empty_like(x)
         grad_skip = torch.empty_like(x) if ctx.has_skip else None
         grad_gamma = torch.empty(c, dtype=torch.float32, device=x.device)
         grad_beta = torch.empty(c, dtype=torch.float32, device=x.device)
-        capi.bn_relu_backward(x, y, grad_y, weight, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta,
-                              _bn_workspace(c, x.device), n * h * w, c)
+        if ctx.has_skip:
+            capi.bn_relu_backward(x, y_or_beta, grad_y, weight, save_mean, save_rstd, grad_x, grad_skip, grad_gamma, grad_beta,
+                                  _bn_workspace(c, x.device), n * h * w, c)
+        else:
+            capi.bn_relu_backward_no_skip(x, grad_y, weight, y_or_beta, save_mean, save_rstd, grad_x, grad_gamma, grad_beta,
+                                          _bn_workspace(c, x.device), n * h * w, c)
         return grad_x, grad_skip, grad_gamma, grad_beta, None, None, None, None, None, None
 
 

@@ -289,6 +289,13 @@ int bb_bn_relu_backward(const void* x, const void* y, const void* grad_y, const 
                         float* grad_gamma, float* grad_beta, float* workspace, int64_t rows,
                         int channels, void* stream);
 
+/* The backward pass of a layer WITHOUT a residual input (conv -> BatchNorm2d -> ReLU, network.py:78-92 and the first
+ * half of ResidualBlock, :24-27): the ReLU mask [y > 0] is recomputed from x with the forward's own affine pair
+ * (y = relu(x * gamma * rstd + (beta - mean * gamma * rstd))), so y is not read back: 5 activation passes instead of 7. */
+int bb_bn_relu_backward_no_skip(const void* x, const void* grad_y, const float* gamma, const float* beta,
+                                const float* save_mean, const float* save_rstd, void* grad_x, float* grad_gamma,
+                                float* grad_beta, float* workspace, int64_t rows, int channels, void* stream);
+
 /* GAE and returns (RolloutBuffer.compute_returns_and_advantages, src/agents/ppo.py:141-169),
  * reverse scan over T, float32, same operation order as the reference (bit-identical).
  *   rewards, values, dones: device f32[T*N] time-major; last_values device f32[N]

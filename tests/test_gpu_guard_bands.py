@@ -136,5 +136,11 @@ def test_batchnorm_kernels_stay_inside_their_buffers(torch, rows, ch):
     ws = A.alloc((capi.bn_workspace_size(ch),), torch.float32)
     capi.bn_relu_forward(x, skip, gamma, beta, None, rm, rv, 0.1, 1e-5, True, y, sm, sr, ws, rows, ch)
     capi.bn_relu_backward(x, y, dy, gamma, sm, sr, dx, dsk, dg, db, ws, rows, ch)
+    dx2, dg2, db2 = A.alloc((rows, ch), torch.bfloat16), A.alloc((ch,), torch.float32), A.alloc((ch,), torch.float32)
+    capi.bn_relu_forward(x, None, gamma, beta, None, rm, rv, 0.1, 1e-5, True, y, sm, sr, ws, rows, ch)
+    capi.bn_relu_backward_no_skip(x, dy, gamma, beta, sm, sr, dx2, dg2, db2, ws, rows, ch)
+    # same result as the variant that reads the ReLU mask from y
+    capi.bn_relu_backward(x, y, dy, gamma, sm, sr, dx, None, dg, db, ws, rows, ch)
     A.check()
+    assert torch.equal(dx, dx2) and torch.equal(dg, dg2) and torch.equal(db, db2)
     assert torch.isfinite(y.float()).all() and torch.isfinite(dx.float()).all()

@@ -98,5 +98,7 @@ for _ in range(REP):
     capi.bn_relu_forward(x, skip, gamma, beta, None, rm, rv, 0.1, 1e-5, True, y, sm, sr, ws, rows, ch)
 for _ in range(REP):
     capi.bn_relu_backward(x, y, dy, gamma, sm, sr, dx, dsk, dg, db, ws, rows, ch)
+for _ in range(REP):
+    capi.bn_relu_backward_no_skip(x, dy, gamma, beta, sm, sr, dx, dg, db, ws, rows, ch)
 torch.cuda.synchronize()
 print("ok")
