@@ -220,3 +220,26 @@ def test_flat_bucket_clip_matches_torch_clip_grad_norm():
         for a, b in zip(lin.parameters(), ref.parameters()):
             assert a.grad.data_ptr() >= bucket.flat.data_ptr()          # still views of the bucket
             torch.testing.assert_close(a.grad, b.grad)
+
+
+def test_cpulist_parser_and_numa_binding_never_raises():
+    """dist.pin_to_gpu_numa is best effort: on a box without NVML / sysfs topology it reports why and
+    leaves the affinity alone."""
+    import os
+    from bbgpu import dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert dist._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    info = dist.pin_to_gpu_numa(0, 1)
+    assert isinstance(info, dict) and ("error" in info or info.get("cpus"))
+    if "error" in info:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
+
+
+def test_shard_is_even_and_contiguous():
+    from bbgpu import dist
+    offs = [dist.shard(512, r, 8) for r in range(8)]
+    assert offs == [(64 * r, 64) for r in range(8)]
+    assert dist.shard(9, 0, 2) == (0, 5) and dist.shard(9, 1, 2) == (5, 4)     # train.py refuses such a job
