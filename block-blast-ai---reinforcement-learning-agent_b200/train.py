@@ -186,6 +186,8 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
                    "max_score": smax, "best_score": max(best_score, avg_score), "avg_length": lsum / cnt if cnt else 0.0,
                    "episodes": cnt, "wall_s": elapsed, "avg_score_10_updates": avg10, **metrics}
             history.append(row)
+            stop = bool((max_updates and num_updates >= max_updates) or (max_wall_s and elapsed >= max_wall_s) or
+                        (target_score and len(recent) == 10 and avg10 >= target_score) or global_step >= total_timesteps)
             if rank == 0:
                 if avg_score > best_score:
                     # snapshot the weights on the device now (cheap), write best.pt at most every few seconds:
@@ -195,7 +197,7 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
                 if best_state is not None and time.time() - best_saved_at > best_every_s:
                     agent.save(os.path.join(ckpt_dir, "best.pt"), network_state=best_state)
                     best_state, best_saved_at = None, time.time()
-                if num_updates % log_interval == 0 or num_updates <= 10 or ours.get("log_every_update"):
+                if num_updates % log_interval == 0 or num_updates <= 10 or ours.get("log_every_update") or stop:
                     logger.log(row, global_step)
                     if tb_logger is not None:
                         tb_logger.log_metrics(tensorboard_tags(row), global_step)
