@@ -186,10 +186,11 @@ cudaError_t bb_launch_gather_minibatch(const int64_t* index, int64_t B, int64_t 
 }
 
 // ------------------------------------------------------------------------------------ K3
-// 8 lanes per row, 4 rows per warp.  Lane l of a row group owns the 24 actions
+// Backward / loss kernels: 8 lanes per row, 4 rows per warp; lane l of a row group owns the 24 actions
 //     a(l,k,c) = 32k + 4l + c        k = 0..5, c = 0..3      (register index i = 4k + c)
-// i.e. the k-th 128-bit load of the group is one contiguous 128 B (f32) run.  Everything else
-// is per-lane arithmetic plus 3-step butterflies inside the 8-lane group.  Maths (network.py:172-262):
+// i.e. the k-th 128-bit load of the group is one contiguous 128 B (f32) run.  The forward kernel uses 4 lanes
+// per row (see below).  Everything else is per-lane arithmetic plus butterflies inside the group.
+// Maths (network.py:172-262):
 //   e_i = 2^((z_i - m) log2 e)        one FFMA + one MUFU per action; masked actions carry z = -1e30,
 //                                     so e_i is exactly 0 and every product with it stays finite
 //   S = sum e_i,  log p_a = (z_a - m) - log S, clamped to [log eps, log(1 - eps)]   (torch Categorical
@@ -270,33 +271,98 @@ __device__ __forceinline__ bool k3_action_valid(const uint64_t* __restrict__ mas
     return (__ldg(mask + (int64_t)(a >> 6) * stride + row) >> (a & 63)) & 1ull;
 }
 
-// MODE 0 sample, 1 argmax, 2 evaluate the given actions; ENT: also write the masked entropy
+// ---- forward: 4 lanes per row, 8 rows per warp.  Lane l of a row group owns the 48 actions
+//     a(l,k,c) = 16k + 4l + c        k = 0..11, c = 0..3     (register index i = 4k + c)
+// (the k-th load of the group is one contiguous 64 B (f32) / 32 B (bf16) run).  With 8 lanes per row the
+// per-lane fixed work (Philox, mask unpack, prefix scan, logs: ~270 instructions) was paid eight times per
+// row and outweighed the 24 x ~10 instructions of per-action arithmetic; four lanes halve that share.
+// Warps walk the rows grid-stride, and one Philox evaluation per lane serves FOUR trips: lane 4g + i draws
+// the uniform of row group g for trip j + i, the group picks it up with a shuffle (same stream position as
+// before: keyed by seed, global row id and call counter only).
+__device__ __forceinline__ float grp4_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float grp4_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// mask bits of this lane's 48 actions: bit (4k + c) = action 16k + 4l + c; plane p holds k = 4p .. 4p+3
+__device__ __forceinline__ uint64_t k3_lane_mask4(const uint64_t* __restrict__ mask, int64_t stride, int64_t row, int l) {
+    uint64_t mb = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const uint64_t w = __ldg(mask + (int64_t)p * stride + row) >> (4 * l);
+        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+        // nibbles at bits 0 and 16 of each half -> one byte per half
+        const uint32_t b = (lo & 0xFu) | ((lo >> 12) & 0xF0u) | ((hi & 0xFu) << 8) | ((hi >> 4) & 0xF000u);
+        mb |= (uint64_t)b << (16 * p);
+    }
+    return mb;
+}
+
+// MODE 0 sample, 1 argmax, 2 evaluate the given actions; ENT: also write the masked entropy.
+// bf16 logits: 6 blocks per SM (80 registers) — the kernel is bound by the half-rate ALU pipe (select, max,
+// compare, count, bf16 unpack: ~4 of the ~10 instructions per action) and by latency at 5 warps per
+// scheduler; measured (tools/time_k3.py, sustained clocks) bf16 + entropy 83.5 -> 70.9 us with the bound,
+// f32 85.6 -> 92.8 us, so f32 stays at 5 blocks (96 registers).
 template <bool BF16, int MODE, bool ENT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BF16 ? 6 : 5)
 bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restrict__ mask, int64_t stride,
                         uint64_t seed, uint64_t call_counter, int32_t* __restrict__ action,
                         float* __restrict__ logp_out, float* __restrict__ ent_out, int64_t n, int64_t row_offset,
                         const uint64_t* __restrict__ counter_dev) {
     const int lane = threadIdx.x & 31;
-    const int l = lane & 7;                       // lane inside the row group
-    const int64_t row_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int l = lane & 3;                       // lane inside the row group
+    const int g = lane >> 2;                      // row group of the warp
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t ctr = MODE == 0 ? call_counter + (counter_dev ? *counter_dev : 0ull) : 0ull;
+    uint32_t ubatch = 0;                          // Philox word of (group g, trip j - (j & 3) + l)
+    int trip = 0;
+    for (int64_t r0 = warp0 * 8; r0 < n; r0 += n_warps * 8, ++trip) {
+    const int64_t row_raw = r0 + g;
     const bool live = row_raw < n;
     const int64_t row = live ? row_raw : n - 1;   // out-of-range groups shadow the last row, never store
+    if (MODE == 0 && (trip & 3) == 0) {
+        // keyed by the GLOBAL row id (env shards on several GPUs draw independent noise) and by a call
+        // counter that may live on the device (a CUDA graph replays the launch with a new value)
+        const uint64_t grow = (uint64_t)(r0 + (int64_t)l * n_warps * 8 + g + row_offset);
+        ubatch = bb_philox((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)ctr, BB_STREAM_SAMPLE,
+                           (uint32_t)seed, (uint32_t)(seed >> 32)).x;
+    }
 
-    float z[24];
-    const uint32_t mb = k3_lane_mask(mask, stride, row, l);
-    k3_load_row<BF16>(logits, row, l, mb, z);
+    float z[48];
+    const uint64_t mb = k3_lane_mask4(mask, stride, row, l);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        float4 v;
+        if (BF16) {
+            const uint2 h = reinterpret_cast<const uint2*>(logits)[row * 48 + k * 4 + l];
+            v.x = __uint_as_float(h.x << 16); v.y = __uint_as_float(h.x & 0xFFFF0000u);
+            v.z = __uint_as_float(h.y << 16); v.w = __uint_as_float(h.y & 0xFFFF0000u);
+        } else {
+            v = reinterpret_cast<const float4*>(logits)[row * 48 + k * 4 + l];
+        }
+        z[4 * k + 0] = v.x; z[4 * k + 1] = v.y; z[4 * k + 2] = v.z; z[4 * k + 3] = v.w;
+    }
+    const uint32_t mlo = (uint32_t)mb, mhi = (uint32_t)(mb >> 32);
     float m = K3_MASKED;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) m = fmaxf(m, z[i]);
-    m = grp_max(m);
+    for (int i = 0; i < 48; ++i) {
+        const bool ok = i < 32 ? ((mlo >> i) & 1u) : ((mhi >> (i - 32)) & 1u);
+        z[i] = ok ? z[i] : K3_MASKED;             // masking (network.py:175-180)
+        m = fmaxf(m, z[i]);
+    }
+    m = grp4_max(m);
     const bool any_valid = m > 0.5f * K3_MASKED;
     const float nm2 = any_valid ? -m * K3_LOG2E : 0.f;
     // z[i] becomes the lane's running sum of e (its local CDF); sz2 = sum e_i d_i log2e
     float run = 0.f, sz2 = 0.f, best = -1.f;
     int bi = 0;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
+    for (int i = 0; i < 48; ++i) {
         const float d2 = fmaf(z[i], K3_LOG2E, nm2);               // (z - m) log2e <= 0
         const float e = k3_ex2(d2);                               // exactly 0 for masked actions
         if (ENT) sz2 = fmaf(e, d2, sz2);
@@ -305,40 +371,35 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         z[i] = run;
     }
     const float lane_tot = run;
-    const float s = grp_sum(lane_tot);
+    const float s = grp4_sum(lane_tot);
 
     int act = 0;
     if (MODE == 2) {
         act = action[row];
     } else if (MODE == 1) {
         // argmax of probs, lowest action index on ties (torch.argmax)
-        int idx = 32 * (bi >> 2) + 4 * l + (bi & 3);
+        int idx = 16 * (bi >> 2) + 4 * l + (bi & 3);
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
+        for (int d = 1; d < 4; d <<= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, d);
             const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
             if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
         act = any_valid ? idx : 0;
     } else {
-        // keyed by the GLOBAL row id (env shards on several GPUs draw independent noise) and by a call
-        // counter that may live on the device (a CUDA graph replays the launch with a new value)
-        const uint64_t grow = (uint64_t)(row + row_offset);
-        const uint64_t ctr = call_counter + (counter_dev ? *counter_dev : 0ull);
-        const BBPhilox4 r = bb_philox((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)ctr,
-                                      BB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+        const uint32_t word = __shfl_sync(0xffffffffu, ubatch, trip & 3, 4);      // this trip's draw of the group
+        const float u = (float)(word >> 8) * (1.0f / 16777216.0f);
         const float t = u * s;
         // inclusive prefix of the lane totals inside the group
         float incl = lane_tot;
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            const float o = __shfl_up_sync(0xffffffffu, incl, d, 8);
+        for (int d = 1; d < 4; d <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, incl, d, 4);
             if (l >= d) incl += o;
         }
         // first lane whose inclusive prefix exceeds t (and that has any probability mass)
-        const unsigned hit = (__ballot_sync(0xffffffffu, incl > t && lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
-        const unsigned nz = (__ballot_sync(0xffffffffu, lane_tot > 0.f) >> (lane & 24)) & 0xFFu;
+        const unsigned hit = (__ballot_sync(0xffffffffu, incl > t && lane_tot > 0.f) >> (lane & 28)) & 0xFu;
+        const unsigned nz = (__ballot_sync(0xffffffffu, lane_tot > 0.f) >> (lane & 28)) & 0xFu;
         // rounding can leave t >= total: fall back to the last lane with mass
         const int L = hit ? (__ffs((int)hit) - 1) : (nz ? (31 - __clz((int)nz)) : 0);
         // inside the lane: the pick is the number of CDF entries <= the local threshold (masked entries
@@ -346,14 +407,14 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         const float tl = t - (incl - lane_tot);
         int cnt = 0;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) cnt += (z[i] <= tl) ? 1 : 0;
-        const int last = 31 - __clz((int)(mb | 1u));
+        for (int i = 0; i < 48; ++i) cnt += (z[i] <= tl) ? 1 : 0;
+        const int last = 63 - __clzll((long long)(mb | 1ull));
         const int pick = cnt < last ? cnt : last;
-        const int idx = 32 * (pick >> 2) + 4 * l + (pick & 3);
-        act = __shfl_sync(0xffffffffu, idx, (lane & 24) | L);
+        const int idx = 16 * (pick >> 2) + 4 * l + (pick & 3);
+        act = __shfl_sync(0xffffffffu, idx, L, 4);
         if (!any_valid) act = 0;
     }
-    const float szt = ENT ? grp_sum(sz2) : 0.f;       // group reduction: executed by all 8 lanes
+    const float szt = ENT ? grp4_sum(sz2) : 0.f;      // group reduction: executed by all lanes
     if (live && l == 0) {
         if (MODE != 2) action[row] = act;
         const float logS = any_valid ? logf(s) : 0.f;
@@ -369,16 +430,32 @@ bb_masked_sample_kernel(const void* __restrict__ logits, const uint64_t* __restr
         }
         if (ENT && ent_out) ent_out[row] = any_valid ? (logS - szt * K3_LN2 / s) : 0.f;
     }
+    }   // rows of this warp
+}
+
+// one resident wave at most (persistent warps walk the rows): blocks per SM from the occupancy calculator
+template <typename K>
+static unsigned k3_wave(K kernel) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+    return (unsigned)((sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 4));
 }
 
 template <bool BF16, int MODE>
-static void k3_launch(bool ent, unsigned grid, cudaStream_t stream, const void* logits, const uint64_t* mask, int64_t stride,
+static void k3_launch(bool ent, int64_t want, cudaStream_t stream, const void* logits, const uint64_t* mask, int64_t stride,
                       uint64_t seed, uint64_t call_counter, int32_t* action, float* logp, float* entropy, int64_t n,
                       int64_t row_offset, const uint64_t* counter_dev) {
-    if (ent)
+    if (ent) {
+        static const unsigned wave = k3_wave(bb_masked_sample_kernel<BF16, MODE, true>);
+        const unsigned grid = (unsigned)(want < (int64_t)wave ? want : wave);
         bb_masked_sample_kernel<BF16, MODE, true><<<grid, 128, 0, stream>>>(logits, mask, stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev);
-    else
+    } else {
+        static const unsigned wave = k3_wave(bb_masked_sample_kernel<BF16, MODE, false>);
+        const unsigned grid = (unsigned)(want < (int64_t)wave ? want : wave);
         bb_masked_sample_kernel<BF16, MODE, false><<<grid, 128, 0, stream>>>(logits, mask, stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev);
+    }
 }
 
 cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const uint64_t* mask,
@@ -386,9 +463,9 @@ cudaError_t bb_launch_masked_sample(const void* logits, int logits_dtype, const 
                                     int32_t* action, float* logp, float* entropy, int64_t n, cudaStream_t stream,
                                     int64_t row_offset, const uint64_t* counter_dev) {
     if (n <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((n * 8 + 127) / 128);
+    const int64_t want = (n + 31) / 32;           // 32 rows per block and trip
     const bool ent = entropy != nullptr;
-#define K3_GO(BF, MD) k3_launch<BF, MD>(ent, grid, stream, logits, mask, mask_stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev)
+#define K3_GO(BF, MD) k3_launch<BF, MD>(ent, want, stream, logits, mask, mask_stride, seed, call_counter, action, logp, entropy, n, row_offset, counter_dev)
     if (logits_dtype == 1) {
         if (mode == 0) K3_GO(true, 0); else if (mode == 1) K3_GO(true, 1); else K3_GO(true, 2);
     } else {

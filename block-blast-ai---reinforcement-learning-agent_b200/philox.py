@@ -86,7 +86,7 @@ def sample_uniforms(seed, call_counter, n_rows):
 
 
 def sample_order():
-    """int64 [192]: the order in which bb_masked_sample accumulates the CDF — lane l of an
-    8-lane row group owns actions 32k + 4l + c (k = 0..5, c = 0..3); lanes are scanned in
+    """int64 [192]: the order in which bb_masked_sample accumulates the CDF — lane l of a
+    4-lane row group owns actions 16k + 4l + c (k = 0..11, c = 0..3); lanes are scanned in
     order, then k, then c."""
-    return np.array([32 * k + 4 * l + c for l in range(8) for k in range(6) for c in range(4)], dtype=np.int64)
+    return np.array([16 * k + 4 * l + c for l in range(4) for k in range(12) for c in range(4)], dtype=np.int64)
