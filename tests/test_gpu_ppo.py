@@ -462,3 +462,37 @@ def test_rollout_runner_rows_replay_through_the_oracle(torch, use_graph):
         m = agent.update(buf, lv, use_graph=use_graph)
         assert all(np.isfinite(v) for v in m.values()) and m["entropy"] > 0.1
     venv.close()
+
+
+@pytest.mark.parametrize("obs_dtype", ["float32", "bfloat16"])
+def test_gather_minibatch_equals_fancy_indexing(torch, obs_dtype):
+    """bb_gather_minibatch (RolloutBuffer.gather) against the reference's own recipe for a minibatch
+    (ppo.py:171-213): flatten (T, N), normalise the advantages over the whole buffer, fancy-index every
+    array with the sample indices — board / piece planes through K2 on the gathered packed words."""
+    from bbgpu import capi
+    from bbgpu.rollout import RolloutBuffer
+    T, N, B = 6, 37, 101
+    g = torch.Generator(device="cuda").manual_seed(3)
+    buf = RolloutBuffer(T, N)
+    buf.boards[:T] = torch.randint(-2 ** 62, 2 ** 62, (T, N), device="cuda", generator=g)
+    buf.pieces[:T] = (torch.randint(0, 37, (T, N), device="cuda", generator=g) | (torch.randint(0, 37, (T, N), device="cuda", generator=g) << 8)
+                      | (torch.randint(0, 37, (T, N), device="cuda", generator=g) << 16) | (torch.randint(0, 8, (T, N), device="cuda", generator=g) << 24)).int()
+    buf.action_masks[:T] = torch.randint(-2 ** 62, 2 ** 62, (T, 3, N), device="cuda", generator=g)
+    buf.actions.copy_(torch.randint(0, 192, (T, N), device="cuda", generator=g))
+    for t in (buf.log_probs, buf.advantages, buf.returns):
+        t.copy_(torch.randn(T, N, device="cuda", generator=g))
+    idx = torch.randint(0, T * N, (B,), device="cuda", generator=g)           # with repeats
+    mean, std = buf.advantages.mean(), buf.advantages.std(unbiased=False)
+    dt = getattr(torch, obs_dtype)
+    out = buf.gather(idx, torch.stack([mean, std]).float(), obs_dtype=dt)
+    torch.cuda.synchronize()
+    t_i, n_i = idx // N, idx % N
+    assert torch.equal(out["actions"], buf.actions[t_i, n_i]) and torch.equal(out["logp"], buf.log_probs[t_i, n_i])
+    assert torch.equal(out["ret"], buf.returns[t_i, n_i])
+    assert torch.equal(out["mask"], buf.action_masks[t_i, :, n_i].t().contiguous())
+    want_adv = (buf.advantages[t_i, n_i] - mean) / (std + 1e-8)
+    torch.testing.assert_close(out["adv"], want_adv, rtol=1e-6, atol=1e-6)
+    ref = torch.empty((B, 4, 8, 8), dtype=dt, device="cuda")
+    capi.unpack_obs(buf.boards[t_i, n_i].contiguous(), buf.pieces[t_i, n_i].contiguous(), out["mask"], B, obs=ref, n=B)
+    assert torch.equal(out["obs"], ref) and out["obs"].dtype == dt
+    assert float(out["obs"][:, 0].float().sum()) == float(sum(bin(int(x) & (2 ** 64 - 1)).count("1") for x in buf.boards[t_i, n_i].tolist()))
