@@ -316,6 +316,7 @@ class PPOAgent:
         if "b200_state" in ck:
             self.network.sample_calls = ck["b200_state"].get("sample_calls", 0)
         self.bucket.rebind()
+        self._graph = None          # a captured minibatch step has the old hyper-parameters baked in
 
     def train(self):
         self.training = True
