@@ -176,8 +176,9 @@ def train(config, resume_path=None, seed=42, progress_callback=None, max_updates
             num_updates += 1
             e_cnt, e_sum, e_max, e_len = runner.episode_stats()
             cnt, ssum, lsum = dist.all_reduce_scalars([e_cnt, e_sum, e_len], device=device)
-            smax = dist.all_reduce_scalars([e_max], op="max", device=device)[0]
-            elapsed = time.time() - t0
+            # the wall clock is reduced too: every rank must take the same stop decision (a rank that leaves the
+            # loop one update early would leave the others waiting in the next gradient all-reduce)
+            smax, elapsed = dist.all_reduce_scalars([e_max, time.time() - t0], op="max", device=device)
             avg_score = ssum / cnt if cnt else 0.0
             recent.append((cnt, ssum))
             del recent[:-10]
