@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--max-updates", type=int, default=None)
     a = ap.parse_args()
     train(load_config(a.config), a.resume, a.seed, max_updates=a.max_updates)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
