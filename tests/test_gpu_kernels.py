@@ -292,7 +292,8 @@ def test_fused_ppo_loss_tail_matches_torch(torch, dtype):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,with_skip", [((96, 64, 8, 8), False), ((64, 128, 8, 8), True), ((7, 128, 8, 8), True),
-                                             ((33, 24, 3, 5), False)])
+                                             ((33, 24, 3, 5), False),
+                                             ((320, 64, 8, 8), True), ((288, 128, 8, 8), False)])
 def test_fused_bn_relu_matches_torch(torch, shape, with_skip):
     """bb_bn_relu_forward/backward (FusedBNReLU) against torch's batch_norm (+ skip) + relu with
     autograd, both on bf16 channels-last activations (network.py:14-31, 78-92), incl. the running
