@@ -243,3 +243,27 @@ def test_shard_is_even_and_contiguous():
     offs = [dist.shard(512, r, 8) for r in range(8)]
     assert offs == [(64 * r, 64) for r in range(8)]
     assert dist.shard(9, 0, 2) == (0, 5) and dist.shard(9, 1, 2) == (5, 4)     # train.py refuses such a job
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU arm of the driver's comparison) runs without a GPU and prints exactly
+    one JSON line with the contract's keys; kind says whether the real reference (oracle/_ref) or the port ran."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 100
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    have_copy = os.path.isdir(os.path.join(root, "oracle", "_ref", "src", "environment"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_copy else "port")
