@@ -423,3 +423,30 @@ def test_network_with_fused_bn_matches_torch_path(torch):
         la, _ = tor_net.trunk(xin)
         lb, _ = fus_net.trunk(xin)
     assert rel(lb.float(), la.float()) < 0.03
+
+
+def test_sampling_noise_is_keyed_by_the_global_row(torch):
+    """K3's Philox stream is (seed, row_offset + row, call counter): a batch sampled in two shards with their
+    global offsets draws exactly what the unsharded batch draws (env shards on several GPUs / ranks), whatever
+    the grid the persistent kernel runs on; a device-resident counter adds to the host one."""
+    from bbgpu import capi
+    g = torch.Generator(device="cuda").manual_seed(12)
+    n = 3001
+    logits = torch.randn(n, 192, device="cuda", generator=g)
+    mask = torch.randint(-2 ** 62, 2 ** 62, (3, n), dtype=torch.int64, device="cuda", generator=g) | 1
+    whole, lp = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, device="cuda")
+    capi.masked_sample(logits, mask, n, 5, 9, 0, whole, lp, None)
+    cut = 1234
+    parts, lps = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, device="cuda")
+    capi.masked_sample(logits[:cut].contiguous(), mask[:, :cut].contiguous(), cut, 5, 9, 0, parts[:cut], lps[:cut], None, 0)
+    capi.masked_sample(logits[cut:].contiguous(), mask[:, cut:].contiguous(), n - cut, 5, 9, 0, parts[cut:], lps[cut:], None, cut)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts) and torch.equal(lp, lps)
+    ctr = torch.tensor([4], dtype=torch.int64, device="cuda")
+    dev_ctr = torch.empty(n, dtype=torch.int32, device="cuda")
+    capi.masked_sample(logits, mask, n, 5, 5, 0, dev_ctr, lp, None, 0, ctr)            # 5 + 4 == 9
+    torch.cuda.synchronize()
+    assert torch.equal(whole, dev_ctr)
+    other = torch.empty(n, dtype=torch.int32, device="cuda")
+    capi.masked_sample(logits, mask, n, 5, 9, 0, other, lp, None, 7)                   # shifted rows: different draws
+    assert (other != whole).float().mean() > 0.5
